@@ -1,0 +1,211 @@
+/*
+ * jat_b200.h -- C ABI of libjat_b200.so: hand-written sm_100a kernels for the JaT-AudioSR DiT
+ * denoiser hot path (DiT forward inside the flow-matching Euler/CFG sampler).
+ *
+ * The reference (HUSRCF/JaTSR-Just-audio-transformer-super-solution) is pure PyTorch and has no
+ * FFI / plugin layer of its own; its boundary for this path is the nn.Module
+ * `JaT_AudioSR_V2/V3.forward(x_t, t, x_cond)` (src/models/jat_audiosr_v2.py:399-448,
+ * src/models/jat_audiosr_v3.py:422-471) plus the free function `flow_matching_sample`
+ * (infer_test_v3m2.py:108-185). The Python mirror of that surface lives in
+ * `jatsr-just-audio-transformer-super-solution_b200/{models,sampler}.py`; every device operation it
+ * performs goes through the entry points below (ctypes binding in `_lib.py`).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; nothing here synchronises the device or
+ *     allocates device memory; all buffers are owned by the caller;
+ *   - return value: 0 = ok; > 0 = a `cudaError_t`; < 0 = JAT_ERR_* (argument / shape errors);
+ *     `jat_last_error()` returns a human-readable message for the calling thread;
+ *   - row-major everywhere; "bf16" = __nv_bfloat16 bits (uint16_t), "f32" = float;
+ *   - token rows: m = b * tokens_per_batch + n  (b = batch item, n = token index = RoPE position).
+ */
+#ifndef JAT_B200_H
+#define JAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAT_ABI_VERSION 1
+
+#define JAT_ERR_BAD_ARG (-1)      /* null pointer, negative size, unsupported enum */
+#define JAT_ERR_BAD_SHAPE (-2)    /* shape not supported by the kernels (see each function) */
+#define JAT_ERR_NO_DRIVER (-3)    /* cuTensorMapEncodeTiled could not be resolved */
+#define JAT_ERR_TENSORMAP (-4)    /* cuTensorMapEncodeTiled failed */
+#define JAT_ERR_SEQ_TOO_LONG (-5) /* token count > max_len (reference raises ValueError, jat_audiosr_v2.py:428) */
+
+typedef struct jat_ctx jat_ctx; /* opaque: device id, SM count, TMA descriptor cache */
+
+int jat_abi_version(void);
+const char* jat_last_error(void);
+/* Binds to CUDA device `device`, resolves the driver entry points; no device memory is allocated. */
+int jat_create(int device, jat_ctx** out);
+void jat_destroy(jat_ctx* ctx);
+int jat_sm_count(const jat_ctx* ctx);
+
+/* ----------------------------------------------------------------------------------------------
+ * Normalisation kinds (jat_audiosr_v2.py:242,245,361 vs jat_audiosr_v3.py:261,264,384)
+ * -------------------------------------------------------------------------------------------- */
+#define JAT_NORM_LAYERNORM 0 /* nn.LayerNorm(D, elementwise_affine=False, eps), biased variance */
+#define JAT_NORM_RMSNORM 1   /* nn.RMSNorm(D, eps) with learnable weight[D] */
+
+/* Fused AdaLN: out[m,:] = norm(x[m,:]) * (1 + scale[b,:]) + shift[b,:], b = m / tokens_per_batch.
+ * Replaces norm1/norm2 + modulate (jat_audiosr_v2.py:278-279,284-285) and, with shift == scale ==
+ * NULL, the un-modulated final norm (jat_audiosr_v2.py:361).
+ *   x      f32 [M, D]      out  bf16 [M, D]      weight f32 [D] (RMSNorm only, else NULL)
+ *   shift/scale f32, element (b, d) at  ptr[b * mod_batch_stride + d]  (stride 0 = one t for all b)
+ * D % 4 == 0, D <= 4096. */
+int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift, const float* scale,
+                            int64_t mod_batch_stride, const float* weight, int norm_kind, float eps, int M, int D,
+                            int tokens_per_batch, void* stream);
+
+/* Patchify + concat + cast: builds the bf16 A operand of patch_embed.proj.0
+ * (jat_audiosr_v2.py:411-421 pad+cat, :225-227 reshape/permute).
+ *   x_t, x_cond f32 [B, C, T]  ->  out bf16 [B * N, 2*C*P],  N = ceil(T / P)
+ *   out[b*N + n, c*P + p]       = x_t  [b, c, n*P + p]   (0 when n*P+p >= T)
+ *   out[b*N + n, (C + c)*P + p] = x_cond[b, c, n*P + p]
+ * x_cond == NULL means an all-zero condition (the CFG unconditional half, infer_test_v3m2.py:142).
+ * cond_batch: number of batch items present in x_cond; items b >= cond_batch read zeros
+ * (lets the sampler pass [z ; z] x [cond ; 0] without materialising the cats of :154-156).
+ * xt_batch: number of batch items present in x_t; item b reads x_t[b % xt_batch].
+ * P must be 4. */
+int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
+                      void* out_bf16, int B, int C, int T, int P, void* stream);
+
+/* Sinusoidal timestep features (TimeEmbedding.forward, jat_audiosr_v2.py:177-190), bf16 output
+ * (the A operand of t_embedder.1):  out[b, i] = sin(t[b] * f_i), out[b, half + i] = cos(t[b] * f_i),
+ * f_i = exp(-i * ln(1e4) / (half - 1)), half = D / 2.   t f32 [B] -> out bf16 [B, D]. */
+int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf16, int B, int D, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM GEMM fed by TMA:  acc[M, N] = A[M, K] (bf16, row pitch lda) * W[N, K]^T (bf16,
+ * nn.Linear layout, row pitch ldw), fp32 accumulation in tensor memory, fused epilogue.
+ * Requirements: K % 64 == 0, N % 128 == 0, lda/ldw % 8 == 0, 16-byte aligned pointers.
+ * -------------------------------------------------------------------------------------------- */
+#define JAT_EPI_BIAS_ACT 0      /* out = act(acc + bias)                  (Linear [+GELU|SiLU])      */
+#define JAT_EPI_QKV_ROPE 1      /* out = RoPE(acc) on columns < rope_cols (q_proj/k_proj/v_proj+RoPE) */
+#define JAT_EPI_GATE_RESIDUAL 2 /* out(f32, in place) += gate[b,:] * (acc + bias)   (adaLN-Zero gate) */
+#define JAT_EPI_UNPATCHIFY 3    /* out[b, c, n*P+p] = acc[m, c*P+p] + bias  (final Linear+unpatchify) */
+
+#define JAT_ACT_NONE 0
+#define JAT_ACT_GELU_ERF 1 /* nn.GELU() default (exact erf form), jat_audiosr_v2.py:206,249 */
+#define JAT_ACT_SILU 2     /* nn.SiLU(), jat_audiosr_v2.py:344,257 */
+
+#define JAT_DTYPE_F32 0
+#define JAT_DTYPE_BF16 1
+
+typedef struct jat_gemm_epilogue {
+    int32_t kind;      /* JAT_EPI_* */
+    int32_t act;       /* JAT_ACT_*   (BIAS_ACT only) */
+    int32_t out_dtype; /* JAT_DTYPE_* (BIAS_ACT only; QKV_ROPE is bf16; GATE_RESIDUAL/UNPATCHIFY f32) */
+    int32_t tokens_per_batch; /* N tokens per batch item: b = m / N, RoPE position = m % N */
+    const float* bias;        /* f32 [N] or NULL */
+    void* out;                /* [M, ldo] (UNPATCHIFY: f32 [B, C, T_out]) */
+    int64_t ldo;              /* output row pitch in elements */
+    const float* gate;        /* GATE_RESIDUAL: gate[b * gate_batch_stride + n] */
+    int64_t gate_batch_stride;
+    const float* rope_cos; /* QKV_ROPE: cos_cached / sin_cached f32 [max_pos, 64] (jat_audiosr_v2.py:60-68) */
+    const float* rope_sin;
+    int32_t rope_cols; /* QKV_ROPE: columns [0, rope_cols) are 64-wide heads to rotate (Q and K) */
+    int32_t patch_len; /* UNPATCHIFY: P (must be 4) */
+    int32_t t_out;     /* UNPATCHIFY: cropped length T (<= tokens_per_batch * P) */
+    int32_t reserved;
+} jat_gemm_epilogue;
+
+/* cta_pair: 0 = one CTA per 128-row tile (tcgen05 cta_group::1), 1 = CTA pair per 256-row tile
+ * (cta_group::2, halves the per-SM B-operand traffic). block_n: 128 or 256 (0 = library picks). */
+int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                  const jat_gemm_epilogue* epi, int cta_pair, int block_n, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * GQA attention (GroupedQueryAttention.forward, jat_audiosr_v2.py:141-164, eval mode):
+ *   out[b, n, h*64 : h*64+64] = softmax(Q_h K_g^T / sqrt(64)) V_g,  g = h / (Hq / Hkv)
+ * on the packed projection buffer written by the QKV_ROPE GEMM:
+ *   qkv bf16 [B * N, (Hq + 2*Hkv) * 64] = [ Q heads | K heads | V heads ],   out bf16 [B * N, Hq*64].
+ * No mask, bidirectional. K/V of one KV head are staged in shared memory once per CTA and reused
+ * by the Hq/Hkv query heads of the group. head_dim must be 64; N <= 512.
+ * -------------------------------------------------------------------------------------------- */
+int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, int B, int N, int Hq, int Hkv,
+                          int head_dim, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Fused sampler update (infer_test_v3m2.py:161-179): CFG combine + x-prediction -> velocity + Euler.
+ *   x   = x_u + cfg_scale * (x_c - x_u)            (x = x_c when x_u == NULL, i.e. cfg_scale == 1)
+ *   z  <- z + (x - z) / (1 - t + 1e-5) * dt         if t < 0.999, else z <- x
+ * t and dt are read from DEVICE memory (t_dt[2*step], t_dt[2*step+1]) so a captured CUDA graph can be
+ * replayed for every step; all tensors f32 with `numel` elements, updated in place on z.
+ * -------------------------------------------------------------------------------------------- */
+int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, const float* x_u, float cfg_scale,
+                         const float* t_dt, int step, int64_t numel, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Whole DiT forward (JaT_AudioSR_V2/V3.forward, eval mode) as one host call that enqueues every
+ * kernel on `stream`. All weights are the caller's packed bf16 copies (see engine.py: pack order).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct jat_dit_weights {
+    int32_t hidden, depth, n_q_heads, n_kv_heads, head_dim, mlp_hidden, bottleneck, channels, patch_len,
+        norm_kind, max_len, rope_max_pos;
+    float norm_eps;
+    int32_t reserved;
+    const void* pe_w1;   /* bf16 [bottleneck, 2*C*P]   patch_embed.proj.0.weight */
+    const float* pe_b1;  /* f32  [bottleneck] */
+    const void* pe_w2;   /* bf16 [hidden, bottleneck]  patch_embed.proj.2.weight */
+    const float* pe_b2;  /* f32  [hidden] */
+    const void* te_w1;   /* bf16 [hidden, hidden]      t_embedder.1 */
+    const float* te_b1;
+    const void* te_w2;   /* bf16 [hidden, hidden]      t_embedder.3 */
+    const float* te_b2;
+    const void* ada_w;   /* bf16 [depth * 6 * hidden, hidden]  blocks.i.adaLN_modulation.1.weight stacked */
+    const float* ada_b;  /* f32  [depth * 6 * hidden] */
+    const void* const* wqkv; /* host array [depth] of bf16 [(Hq+2Hkv)*64, hidden]  (q_proj|k_proj|v_proj rows) */
+    const void* const* wo;   /* host array [depth] of bf16 [hidden, hidden]        out_proj */
+    const void* const* w1;   /* host array [depth] of bf16 [mlp_hidden, hidden]    mlp.0 */
+    const float* const* b1;  /* host array [depth] of f32  [mlp_hidden] */
+    const void* const* w2;   /* host array [depth] of bf16 [hidden, mlp_hidden]    mlp.3 */
+    const float* const* b2;  /* host array [depth] of f32  [hidden] */
+    const float* const* norm1_w; /* host array [depth] of f32 [hidden] (RMSNorm) or NULL */
+    const float* const* norm2_w;
+    const float* final_norm_w; /* f32 [hidden] (RMSNorm) or NULL */
+    const void* final_w;       /* bf16 [C*P, hidden]  final_layer.1.weight */
+    const float* final_b;      /* f32  [C*P] */
+    const float* rope_cos;     /* f32 [rope_max_pos, 64] */
+    const float* rope_sin;
+} jat_dit_weights;
+
+typedef struct jat_dit_workspace {
+    /* all device buffers, sized for M = B * N token rows (N = ceil(T / P)) */
+    void* patches;  /* bf16 [M, 2*C*P] */
+    void* pe_hid;   /* bf16 [M, bottleneck] */
+    float* x;       /* f32  [M, hidden]       residual stream */
+    void* h;        /* bf16 [M, hidden]       normalised+modulated GEMM operand */
+    void* qkv;      /* bf16 [M, (Hq+2Hkv)*64] */
+    void* attn;     /* bf16 [M, hidden] */
+    void* mlp_hid;  /* bf16 [M, mlp_hidden] */
+    void* t_feat;   /* bf16 [Bt, hidden]      sinusoid features */
+    void* t_hid;    /* bf16 [Bt, hidden] */
+    void* t_act;    /* bf16 [Bt, hidden]      SiLU(t_emb) */
+    float* mod;     /* f32  [Bt, depth*6*hidden]  all blocks' shift/scale/gate */
+    float* block_out; /* optional f32 [depth, M, hidden] per-block residual snapshots for parity tests, or NULL */
+} jat_dit_workspace;
+
+/* Timestep path only: t f32 [Bt] -> ws->mod [Bt, depth*6*hidden] (t_embedder + every block's
+ * adaLN_modulation, jat_audiosr_v2.py:341-346,256-259,274-275). */
+int jat_dit_modulation(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const float* t, int Bt,
+                       void* stream);
+
+/* Token path: x_t/x_cond f32 -> out f32 [B, C, T]; modulation rows taken from `mod`
+ * (row b * mod_batch_stride; stride 0 = shared t). Semantics of xt_batch / cond_batch as in
+ * jat_patchify_cast. */
+int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const float* x_t,
+                           int xt_batch, const float* x_cond, int cond_batch, const float* mod,
+                           int64_t mod_batch_stride, float* out, int B, int T, void* stream);
+
+/* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
+int64_t jat_launch_count(const jat_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAT_B200_H */

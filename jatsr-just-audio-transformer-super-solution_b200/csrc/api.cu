@@ -1,0 +1,423 @@
+// extern "C" surface of libjat_b200.so (see include/jat_b200.h): argument checking, TMA descriptor
+// construction, kernel dispatch, and the host-side launch plan of the whole DiT forward.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "../../include/jat_b200.h"
+#include "attention_gqa.cuh"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace jat;
+
+// ------------------------------------------------------------------------------------------------ ctx
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct jat_ctx {
+    int device;
+    int sm_count;
+    PFN_encodeTiled encode;
+    std::atomic<long long> launches;
+    int gemm_cta_pair;  // default tile configuration (overridable per call)
+    int gemm_block_n;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+#define JAT_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+#define JAT_TRY(call)              \
+    do {                           \
+        int r__ = (call);          \
+        if (r__ != 0) return r__;  \
+    } while (0)
+
+extern "C" int jat_abi_version(void) { return JAT_ABI_VERSION; }
+extern "C" const char* jat_last_error(void) { return g_err; }
+
+extern "C" int jat_create(int device, jat_ctx** out) {
+    if (!out) return fail(JAT_ERR_BAD_ARG, "jat_create: out == NULL");
+    *out = nullptr;
+    JAT_CUDA(cudaSetDevice(device));
+    JAT_CUDA(cudaFree(0));
+    cudaDeviceProp prop;
+    JAT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(JAT_ERR_BAD_ARG, "jat_create: device %d is sm_%d%d, this library is sm_100a only",
+                                      device, prop.major, prop.minor);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    JAT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(JAT_ERR_NO_DRIVER, "cuTensorMapEncodeTiled not found");
+    jat_ctx* c = new (std::nothrow) jat_ctx();
+    if (!c) return fail(JAT_ERR_BAD_ARG, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->encode = (PFN_encodeTiled)fn;
+    c->launches.store(0);
+    c->gemm_cta_pair = 0;
+    c->gemm_block_n = 0;
+    *out = c;
+    return 0;
+}
+extern "C" void jat_destroy(jat_ctx* ctx) { delete ctx; }
+extern "C" int jat_sm_count(const jat_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t jat_launch_count(const jat_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
+extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    if (block_n != 0 && block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "block_n must be 0/128/256");
+    ctx->gemm_cta_pair = cta_pair ? 1 : 0;
+    ctx->gemm_block_n = block_n;
+    return 0;
+}
+
+static int post_launch(jat_ctx* ctx, const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "launch %s: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    ctx->launches.fetch_add(1);
+    return 0;
+}
+
+// 2D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch ld elements; box = box_rows x 64
+// columns (128 bytes), 128-byte swizzle, out-of-bounds elements read as zero.
+static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0)
+        return fail(JAT_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a row pitch multiple of 8 elements");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JAT_ERR_TENSORMAP, "cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu ld %llu box_rows %u",
+                                       (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
+static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    int clusters = ctx->sm_count / CG;
+    if (clusters > p.num_tiles) clusters = p.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    return post_launch(ctx, "gemm_tcgen05");
+}
+
+template <int BN, int CG>
+static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                             const jat_gemm_epilogue* e, cudaStream_t s) {
+    switch (e->kind) {
+        case JAT_EPI_BIAS_ACT:
+            if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_F32)
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 0>(ctx, ta, tb, p, s);
+            if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 1>(ctx, ta, tb, p, s);
+            if (e->act == JAT_ACT_GELU_ERF && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_GELU, 1>(ctx, ta, tb, p, s);
+            if (e->act == JAT_ACT_SILU && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_SILU, 1>(ctx, ta, tb, p, s);
+            return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unsupported act/out_dtype combination (%d, %d)", e->act,
+                        e->out_dtype);
+        case JAT_EPI_QKV_ROPE:
+            return launch_gemm<BN, CG, EPI_QKV_ROPE, ACT_NONE, 1>(ctx, ta, tb, p, s);
+        case JAT_EPI_GATE_RESIDUAL:
+            return launch_gemm<BN, CG, EPI_GATE_RESIDUAL, ACT_NONE, 0>(ctx, ta, tb, p, s);
+        case JAT_EPI_UNPATCHIFY:
+            return launch_gemm<BN, CG, EPI_UNPATCHIFY, ACT_NONE, 0>(ctx, ta, tb, p, s);
+    }
+    return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
+}
+
+extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                             const jat_gemm_epilogue* e, int cta_pair, int block_n, void* stream) {
+    if (!ctx || !A || !W || !e || !e->out) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: null argument");
+    if (M <= 0 || N <= 0 || K <= 0) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: non-positive size");
+    if (K % 64 != 0 || N % 128 != 0)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
+    if (cta_pair < 0) cta_pair = ctx->gemm_cta_pair;
+    if (block_n == 0) block_n = ctx->gemm_block_n;
+    if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
+    if (block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: block_n must be 128 or 256");
+    if (N % block_n != 0) block_n = 128;
+    const int cg = cta_pair ? 2 : 1;
+
+    GemmParams p = {};
+    p.M = M; p.N = N; p.K = K;
+    p.num_n_blocks = N / block_n;
+    p.num_k_blocks = K / GEMM_BK;
+    const int rows_per_tile = GEMM_BM * cg;
+    p.num_tiles = ((M + rows_per_tile - 1) / rows_per_tile) * p.num_n_blocks;
+    p.bias = e->bias;
+    p.out = e->out;
+    p.ldo = e->ldo;
+    p.gate = e->gate;
+    p.gate_bstride = e->gate_batch_stride;
+    p.tokens_per_batch = e->tokens_per_batch > 0 ? e->tokens_per_batch : M;
+    p.rope_cos = e->rope_cos;
+    p.rope_sin = e->rope_sin;
+    p.rope_cols = e->rope_cols;
+    p.t_out = e->t_out;
+
+    switch (e->kind) {
+        case JAT_EPI_BIAS_ACT:
+            if (e->ldo % 8 != 0) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: ldo must be a multiple of 8");
+            break;
+        case JAT_EPI_QKV_ROPE:
+            if (!e->rope_cos || !e->rope_sin || e->rope_cols % 64 != 0 || e->ldo % 8 != 0)
+                return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: QKV_ROPE needs cos/sin tables and rope_cols %% 64 == 0");
+            break;
+        case JAT_EPI_GATE_RESIDUAL:
+            if (!e->gate || e->ldo % 4 != 0 || e->gate_batch_stride % 4 != 0)
+                return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: GATE_RESIDUAL needs gate and 16B-aligned pitches");
+            break;
+        case JAT_EPI_UNPATCHIFY:
+            if (e->patch_len != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: UNPATCHIFY supports patch_len 4 only");
+            if (e->t_out <= 0 || e->t_out > p.tokens_per_batch * 4)
+                return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: UNPATCHIFY t_out out of range");
+            break;
+        default:
+            return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
+    }
+
+    CUtensorMap ta, tb;
+    JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
+    JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg)));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (block_n == 256) {
+        if (cg == 1) return dispatch_gemm_epi<256, 1>(ctx, ta, tb, p, e, s);
+        return dispatch_gemm_epi<256, 2>(ctx, ta, tb, p, e, s);
+    }
+    if (cg == 1) return dispatch_gemm_epi<128, 1>(ctx, ta, tb, p, e, s);
+    return dispatch_gemm_epi<128, 2>(ctx, ta, tb, p, e, s);
+}
+
+// ------------------------------------------------------------------------------------------------ AdaLN
+template <int NORM>
+static int launch_adaln(jat_ctx* ctx, const float* x, __nv_bfloat16* out, const float* shift, const float* scale,
+                        long long bstride, const float* weight, float eps, int M, int D, int ntok, cudaStream_t s) {
+    const int nvec = D / 4;
+    const int nv = (nvec + 31) / 32;
+    dim3 grid((M + ADALN_WARPS - 1) / ADALN_WARPS), block(ADALN_WARPS * 32);
+#define JAT_ADALN_CASE(NV)                                                                                       \
+    adaln_norm_modulate_kernel<NV, NORM><<<grid, block, 0, s>>>(x, out, shift, scale, bstride, weight, eps, M, D, ntok)
+    if (nv <= 4) JAT_ADALN_CASE(4);
+    else if (nv <= 8) JAT_ADALN_CASE(8);
+    else if (nv <= 10) JAT_ADALN_CASE(10);
+    else if (nv <= 16) JAT_ADALN_CASE(16);
+    else JAT_ADALN_CASE(32);
+#undef JAT_ADALN_CASE
+    return post_launch(ctx, "adaln_norm_modulate");
+}
+
+extern "C" int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift,
+                                       const float* scale, int64_t mod_batch_stride, const float* weight, int norm_kind,
+                                       float eps, int M, int D, int tokens_per_batch, void* stream) {
+    if (!ctx || !x || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: null argument");
+    if ((shift == nullptr) != (scale == nullptr))
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: shift and scale must both be given or both NULL");
+    if (M <= 0 || D <= 0 || D % 4 != 0 || D > 4096)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_adaln_norm_modulate: need D %% 4 == 0 and D <= 4096 (got %d)", D);
+    if (mod_batch_stride % 4 != 0) return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: mod_batch_stride %% 4 != 0");
+    if (tokens_per_batch <= 0) tokens_per_batch = M;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (norm_kind == JAT_NORM_LAYERNORM)
+        return launch_adaln<0>(ctx, x, (__nv_bfloat16*)out_bf16, shift, scale, mod_batch_stride, nullptr, eps, M, D,
+                               tokens_per_batch, s);
+    if (norm_kind == JAT_NORM_RMSNORM) {
+        if (!weight) return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: RMSNorm needs a weight");
+        return launch_adaln<1>(ctx, x, (__nv_bfloat16*)out_bf16, shift, scale, mod_batch_stride, weight, eps, M, D,
+                               tokens_per_batch, s);
+    }
+    return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: unknown norm_kind %d", norm_kind);
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
+                                 void* out_bf16, int B, int C, int T, int P, void* stream) {
+    if (!ctx || !x_t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_patchify_cast: null argument");
+    if (P != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: patch_len must be 4 (got %d)", P);
+    if (B <= 0 || C <= 0 || T <= 0 || C % PATCH_TC != 0 || xt_batch <= 0 || B > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: need C %% 32 == 0, 0 < B <= 65535");
+    const int N = (T + P - 1) / P;
+    dim3 grid((N + PATCH_TN - 1) / PATCH_TN, 2 * C / PATCH_TC, B);
+    patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, xt_batch, x_cond, cond_batch,
+                                                                 (__nv_bfloat16*)out_bf16, C, T, N);
+    return post_launch(ctx, "patchify_cast");
+}
+
+extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf16, int B, int D, void* stream) {
+    if (!ctx || !t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_timestep_features: null argument");
+    if (B <= 0 || D < 4 || D % 2 != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_timestep_features: bad B/D");
+    dim3 grid((D / 2 + 127) / 128, B);
+    timestep_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out_bf16, B, D);
+    return post_launch(ctx, "timestep_features");
+}
+
+extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, const float* x_u, float cfg_scale,
+                                    const float* t_dt, int step, int64_t numel, void* stream) {
+    if (!ctx || !z || !x_c || !t_dt) return fail(JAT_ERR_BAD_ARG, "jat_cfg_euler_update: null argument");
+    if (numel <= 0 || step < 0) return fail(JAT_ERR_BAD_ARG, "jat_cfg_euler_update: bad numel/step");
+    long long want = (numel / 4 + 255) / 256;
+    long long cap = (long long)ctx->sm_count * 8;
+    int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    cfg_euler_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, x_c, x_u, cfg_scale, t_dt, step,
+                                                                       (long long)numel);
+    return post_launch(ctx, "cfg_euler_update");
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, int B, int N, int Hq, int Hkv,
+                                     int head_dim, void* stream) {
+    if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
+    if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
+    if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: bad B/N/heads");
+    const int NK = (N + 15) / 16 * 16;
+    if (NK > ATT_MAX_NK)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: N = %d tokens > %d not supported by the single-pass kernel", N,
+                    ATT_MAX_NK);
+    AttnParams p = {};
+    p.B = B; p.N = N; p.NK = NK; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
+    if (NK <= 256) { p.kv_box_rows = NK; p.kv_boxes = 1; p.nA = NK; p.nB = 0; }
+    else { p.kv_box_rows = NK / 2; p.kv_boxes = 2; p.nA = NK / 2; p.nB = NK - p.nA; }
+    p.out = (__nv_bfloat16*)out;
+    p.scale_log2e = 0.125f * 1.4426950408889634f;
+    const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
+    CUtensorMap tq, tkv;
+    JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
+    JAT_TRY(make_tmap(ctx, &tkv, qkv, rows, cols, cols, (uint32_t)p.kv_box_rows));
+    static bool configured = false;
+    if (!configured) {
+        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ATT_SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
+    gqa_attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, p);
+    return post_launch(ctx, "gqa_attention_fwd");
+}
+
+// ------------------------------------------------------------------------------------------------ DiT forward plan
+static jat_gemm_epilogue epi_bias_act(const float* bias, void* out, int64_t ldo, int act, int dtype) {
+    jat_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.kind = JAT_EPI_BIAS_ACT; e.act = act; e.out_dtype = dtype; e.bias = bias; e.out = out; e.ldo = ldo;
+    return e;
+}
+
+extern "C" int jat_dit_modulation(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const float* t,
+                                  int Bt, void* stream) {
+    if (!ctx || !w || !ws || !t) return fail(JAT_ERR_BAD_ARG, "jat_dit_modulation: null argument");
+    if (!ws->t_feat || !ws->t_hid || !ws->t_act || !ws->mod) return fail(JAT_ERR_BAD_ARG, "jat_dit_modulation: workspace incomplete");
+    const int D = w->hidden;
+    const int NM = w->depth * 6 * D;
+    JAT_TRY(jat_timestep_features(ctx, t, ws->t_feat, Bt, D, stream));
+    jat_gemm_epilogue e1 = epi_bias_act(w->te_b1, ws->t_hid, D, JAT_ACT_SILU, JAT_DTYPE_BF16);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_feat, D, w->te_w1, D, Bt, D, D, &e1, -1, 0, stream));
+    // adaLN_modulation = SiLU -> Linear: t_emb is only ever consumed through that SiLU, so fuse it here.
+    jat_gemm_epilogue e2 = epi_bias_act(w->te_b2, ws->t_act, D, JAT_ACT_SILU, JAT_DTYPE_BF16);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_hid, D, w->te_w2, D, Bt, D, D, &e2, -1, 0, stream));
+    jat_gemm_epilogue e3 = epi_bias_act(w->ada_b, ws->mod, NM, JAT_ACT_NONE, JAT_DTYPE_F32);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_act, D, w->ada_w, D, Bt, NM, D, &e3, -1, 0, stream));
+    return 0;
+}
+
+extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
+                                      const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
+                                      const float* mod, int64_t mod_batch_stride, float* out, int B, int T,
+                                      void* stream) {
+    if (!ctx || !w || !ws || !x_t || !mod || !out) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_tokens: null argument");
+    const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
+    const int N = (T + P - 1) / P;
+    if (N > w->max_len) return fail(JAT_ERR_SEQ_TOO_LONG, "Sequence length %d exceeds max_len %d", N, w->max_len);
+    if (N > w->rope_max_pos) return fail(JAT_ERR_SEQ_TOO_LONG, "Sequence length %d exceeds RoPE table %d", N, w->rope_max_pos);
+    if (w->head_dim != 64) return fail(JAT_ERR_BAD_SHAPE, "head_dim must be 64");
+    const int M = B * N;
+    const int QKV = (w->n_q_heads + 2 * w->n_kv_heads) * 64;
+    const int KIN = 2 * C * P;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    JAT_TRY(jat_patchify_cast(ctx, x_t, xt_batch, x_cond, cond_batch, ws->patches, B, C, T, P, stream));
+    jat_gemm_epilogue e = epi_bias_act(w->pe_b1, ws->pe_hid, BD, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->patches, KIN, w->pe_w1, KIN, M, BD, KIN, &e, -1, 0, stream));
+    e = epi_bias_act(w->pe_b2, ws->x, D, JAT_ACT_NONE, JAT_DTYPE_F32);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->pe_hid, BD, w->pe_w2, BD, M, D, BD, &e, -1, 0, stream));
+
+    for (int i = 0; i < w->depth; ++i) {
+        const float* m = mod + (int64_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, ws->h, m, m + D, mod_batch_stride,
+                                        w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind, w->norm_eps, M, D, N, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_QKV_ROPE; e.out = ws->qkv; e.ldo = QKV; e.tokens_per_batch = N;
+        e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (w->n_q_heads + w->n_kv_heads) * 64;
+        JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
+        JAT_TRY(jat_gqa_attention_fwd(ctx, ws->qkv, ws->attn, B, N, w->n_q_heads, w->n_kv_heads, 64, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
+        e.gate = m + 2 * D; e.gate_batch_stride = mod_batch_stride;
+        JAT_TRY(jat_gemm_bf16(ctx, ws->attn, D, w->wo[i], D, M, D, D, &e, -1, 0, stream));
+
+        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, ws->h, m + 3 * D, m + 4 * D, mod_batch_stride,
+                                        w->norm2_w ? w->norm2_w[i] : nullptr, w->norm_kind, w->norm_eps, M, D, N, stream));
+        e = epi_bias_act(w->b1[i], ws->mlp_hid, F, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
+        JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->w1[i], D, M, F, D, &e, -1, 0, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N; e.bias = w->b2[i];
+        e.gate = m + 5 * D; e.gate_batch_stride = mod_batch_stride;
+        JAT_TRY(jat_gemm_bf16(ctx, ws->mlp_hid, F, w->w2[i], F, M, D, F, &e, -1, 0, stream));
+        if (ws->block_out)
+            JAT_CUDA(cudaMemcpyAsync(ws->block_out + (int64_t)i * M * D, ws->x, (size_t)M * D * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, ws->h, nullptr, nullptr, 0, w->final_norm_w, w->norm_kind, w->norm_eps, M,
+                                    D, N, stream));
+    memset(&e, 0, sizeof(e));
+    e.kind = JAT_EPI_UNPATCHIFY; e.out = out; e.bias = w->final_b; e.tokens_per_batch = N; e.patch_len = P; e.t_out = T;
+    JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->final_w, D, M, C * P, D, &e, -1, 0, stream));
+    return 0;
+}

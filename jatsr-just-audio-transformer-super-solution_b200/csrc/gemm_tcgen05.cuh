@@ -1,0 +1,358 @@
+// tcgen05 / TMEM GEMM fed by TMA, with the DiT block's elementwise work fused into the epilogue.
+//
+//   acc[M, N] = A[M, K] * W[N, K]^T     A, W bf16 K-major (nn.Linear weight layout), fp32 accumulate
+//
+// Replaces the cuBLAS calls + separate bias / GELU / RoPE / gate / residual / permute kernels the
+// reference issues for patch_embed.proj, t_embedder, adaLN_modulation, q/k/v_proj + RoPE, out_proj,
+// mlp.0/mlp.3 and final_layer (jat_audiosr_v2.py:204-208, 341-346, 256-259, 137-145, 165, 247-253, 281,
+// 286-287, 359-363, 383-397).
+//
+// Structure (one persistent CTA -- or CTA pair -- per SM, 384 threads):
+//   warp 0      TMA producer: A tile [128 x 64] + W tile [BN/CG x 64] per stage, 128B swizzle
+//   warp 1      MMA issuer (one lane): tcgen05.mma kind::f16, M = 128*CG, N = BN, K = 16, accumulators
+//               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld (thread = one accumulator row, 32 columns at a time) -> fused
+//               math -> global stores.  Warpgroup 0 takes columns [0, BN/2), warpgroup 1 the rest.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace jat {
+
+enum { EPI_BIAS_ACT = 0, EPI_QKV_ROPE = 1, EPI_GATE_RESIDUAL = 2, EPI_UNPATCHIFY = 3 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    int num_n_blocks, num_k_blocks, num_tiles;
+    const float* bias;
+    void* out;
+    long long ldo;
+    const float* gate;
+    long long gate_bstride;
+    int tokens_per_batch;
+    const float* rope_cos;
+    const float* rope_sin;
+    int rope_cols;
+    int t_out;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
+
+template <int BN, int CG>
+struct GemmCfg {
+    static constexpr int B_ROWS = BN / CG;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+    if constexpr (ACT == ACT_GELU) return gelu_erf(v);
+    if constexpr (ACT == ACT_SILU) return silu(v);
+    return v;
+}
+
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<BN, CG>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need a 1024-byte aligned base (the swizzle is a function of address bits 4..9).
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + STAGES;
+    uint64_t* bar_tmem_full = bar_empty + STAGES;
+    uint64_t* bar_tmem_empty = bar_tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tmem_full[a], 1);
+            mbar_init(&bar_tmem_empty[a], GEMM_EPI_WARPS * CG);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+                const int a_row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM;
+                const int b_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if constexpr (CG == 1) {
+                        mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
+                        tma_load_2d(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
+                    } else {
+                        // both CTAs' bytes complete on the leader's barrier
+                        if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES * 2);
+                        tma_load_2d_2sm(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
+                        tma_load_2d_2sm(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();  // reconverge before the (warp-aligned) teardown barrier
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                mbar_wait(&bar_tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t a_desc = umma_smem_desc_sw128(sa);
+                        const uint64_t b_desc = umma_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the address field
+                            umma_bf16_ss<CG>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        if constexpr (CG == 1) umma_commit(&bar_empty[stage]);
+                        else umma_commit_2sm(&bar_empty[stage], 0x3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (lane == 0) {
+                    if constexpr (CG == 1) umma_commit(&bar_tmem_full[as]);
+                    else umma_commit_2sm(&bar_tmem_full[as], 0x3);
+                }
+                __syncwarp();
+                if ((as ^= 1) == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+        const int wg = (warp - 4) >> 2;  // column half
+        const int row_in_tile = quad * 32 + lane;
+        constexpr int HALF = BN / 2;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+            const int m = (m_blk * CG + (int)cta_rank) * GEMM_BM + row_in_tile;
+            const bool row_ok = m < p.M;
+            const int n_base = n_blk * BN + wg * HALF;
+            mbar_wait(&bar_tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + wg * HALF);
+
+            if constexpr (EPI == EPI_BIAS_ACT) {
+#pragma unroll 1
+                for (int c = 0; c < HALF / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int n0 = n_base + c * 32;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[j + 0] = apply_act<ACT>(__uint_as_float(v[j + 0]) + b4.x);
+                        f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
+                        f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
+                        f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                    }
+                    if (row_ok) {
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                st_global_v4(o + j, pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                             pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                        } else {
+                            float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_QKV_ROPE) {
+                // 64-wide heads; rotate_half pairs column j with j+32 (jat_audiosr_v2.py:70-91).
+                const int pos = row_ok ? (m % p.tokens_per_batch) : 0;
+                const float* cosr = p.rope_cos + (long long)pos * 64;
+                const float* sinr = p.rope_sin + (long long)pos * 64;
+                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
+#pragma unroll 1
+                for (int hh = 0; hh < HALF / 64; ++hh) {
+                    const int n0 = n_base + hh * 64;
+                    const bool rot = n0 < p.rope_cols;
+#pragma unroll 1
+                    for (int s = 0; s < 2; ++s) {
+                        uint32_t lo[16], hi[16];
+                        tmem_ld_32x16(taddr + hh * 64 + s * 16, lo);
+                        tmem_ld_32x16(taddr + hh * 64 + 32 + s * 16, hi);
+                        tmem_ld_wait();
+                        float ol[16], oh[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rot) {
+                                c4 = __ldg(reinterpret_cast<const float4*>(cosr + s * 16 + j));
+                                s4 = __ldg(reinterpret_cast<const float4*>(sinr + s * 16 + j));
+                            }
+                            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float a = __uint_as_float(lo[j + q]), b = __uint_as_float(hi[j + q]);
+                                ol[j + q] = a * cc[q] - b * ss[q];
+                                oh[j + q] = b * cc[q] + a * ss[q];
+                            }
+                        }
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 8) {
+                                st_global_v4(orow + n0 + s * 16 + j, pack_bf16(ol[j], ol[j + 1]),
+                                             pack_bf16(ol[j + 2], ol[j + 3]), pack_bf16(ol[j + 4], ol[j + 5]),
+                                             pack_bf16(ol[j + 6], ol[j + 7]));
+                                st_global_v4(orow + n0 + 32 + s * 16 + j, pack_bf16(oh[j], oh[j + 1]),
+                                             pack_bf16(oh[j + 2], oh[j + 3]), pack_bf16(oh[j + 4], oh[j + 5]),
+                                             pack_bf16(oh[j + 6], oh[j + 7]));
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_GATE_RESIDUAL) {
+                const int b = row_ok ? (m / p.tokens_per_batch) : 0;
+                const float* grow = p.gate + (long long)b * p.gate_bstride;
+                float* xrow = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo;
+#pragma unroll 1
+                for (int c = 0; c < HALF / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int n0 = n_base + c * 32;
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
+                            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 x4 = *reinterpret_cast<const float4*>(xrow + n0 + j);
+                            x4.x += g4.x * (__uint_as_float(v[j + 0]) + b4.x);
+                            x4.y += g4.y * (__uint_as_float(v[j + 1]) + b4.y);
+                            x4.z += g4.z * (__uint_as_float(v[j + 2]) + b4.z);
+                            x4.w += g4.w * (__uint_as_float(v[j + 3]) + b4.w);
+                            *reinterpret_cast<float4*>(xrow + n0 + j) = x4;
+                        }
+                    }
+                }
+            } else {  // EPI_UNPATCHIFY, patch_len 4: column = c*4 + p -> out[b, c, n*4 + p]
+                const int b = row_ok ? (m / p.tokens_per_batch) : 0;
+                const int n = row_ok ? (m % p.tokens_per_batch) : 0;
+                const int C = p.N >> 2;
+                const int t0 = n * 4;
+                float* obase = reinterpret_cast<float*>(p.out) + (long long)b * C * p.t_out + t0;
+                const bool vec_ok = (p.t_out & 1) == 0;
+#pragma unroll 1
+                for (int c = 0; c < HALF / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int n0 = n_base + c * 32;
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
+                                        r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
+                            float* o = obase + (long long)((n0 + j) >> 2) * p.t_out;
+                            if (vec_ok && t0 + 3 < p.t_out) {
+                                *reinterpret_cast<float2*>(o) = make_float2(r0, r1);
+                                *reinterpret_cast<float2*>(o + 2) = make_float2(r2, r3);
+                            } else {
+                                if (t0 + 0 < p.t_out) o[0] = r0;
+                                if (t0 + 1 < p.t_out) o[1] = r1;
+                                if (t0 + 2 < p.t_out) o[2] = r2;
+                                if (t0 + 3 < p.t_out) o[3] = r3;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // accumulator stage drained -> hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
+                else mbar_arrive_cluster(&bar_tmem_empty[as], 0);
+            }
+            if ((as ^= 1) == 0) aphase ^= 1;
+        }
+    }
+
+    // ---------------------------------------------------------------------- teardown
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace jat

@@ -1,0 +1,122 @@
+"""Torch-tensor wrappers around the C-ABI kernels (one function per `jat_*` entry point).
+
+PyTorch is used for device memory and streams only; every computation below happens inside
+``libjat_b200.so``.  CPU tensors are rejected: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ctx(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("jat_b200 kernels run on CUDA tensors only (no CPU fallback)")
+    return L.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+def adaln_norm_modulate(x, shift=None, scale=None, mod_batch_stride=0, weight=None, norm_kind=L.NORM_LAYERNORM,
+                        eps=1e-6, tokens_per_batch=0, out=None):
+    """x f32 [M, D] -> bf16 [M, D]; shift/scale are f32 tensors (or views) whose row b starts at
+    data_ptr + b * mod_batch_stride elements."""
+    _chk(x, torch.float32, "x")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty(M, D, dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().jat_adaln_norm_modulate(_ctx(x), x.data_ptr(), out.data_ptr(), _p(shift), _p(scale),
+                                             mod_batch_stride, _p(weight), norm_kind, eps, M, D, tokens_per_batch,
+                                             _stream(x.device)))
+    return out
+
+
+def patchify_cast(x_t, x_cond, B, cond_batch=None, out=None, patch_len=4):
+    _chk(x_t, torch.float32, "x_t")
+    xb, Cc, T = x_t.shape
+    N = (T + patch_len - 1) // patch_len
+    if x_cond is not None:
+        _chk(x_cond, torch.float32, "x_cond")
+        if cond_batch is None:
+            cond_batch = x_cond.shape[0]
+    else:
+        cond_batch = 0
+    if out is None:
+        out = torch.empty(B * N, 2 * Cc * patch_len, dtype=torch.bfloat16, device=x_t.device)
+    L.check(L.load().jat_patchify_cast(_ctx(x_t), x_t.data_ptr(), xb, _p(x_cond), cond_batch, out.data_ptr(), B, Cc,
+                                       T, patch_len, _stream(x_t.device)))
+    return out
+
+
+def timestep_features(t, D, out=None):
+    _chk(t, torch.float32, "t")
+    B = t.shape[0]
+    if out is None:
+        out = torch.empty(B, D, dtype=torch.bfloat16, device=t.device)
+    L.check(L.load().jat_timestep_features(_ctx(t), t.data_ptr(), out.data_ptr(), B, D, _stream(t.device)))
+    return out
+
+
+def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, bias=None, out=None,
+         gate=None, gate_batch_stride=0, tokens_per_batch=0, rope_cos=None, rope_sin=None, rope_cols=0,
+         patch_len=4, t_out=0, cta_pair=-1, block_n=0):
+    """acc = A[M,K] @ W[N,K]^T (bf16 in, f32 accumulate) + fused epilogue; returns `out`."""
+    _chk(A, torch.bfloat16, "A")
+    _chk(W, torch.bfloat16, "W")
+    M, K = A.shape
+    N, K2 = W.shape
+    assert K == K2
+    if out is None:
+        if kind == L.EPI_BIAS_ACT:
+            out = torch.empty(M, N, dtype=torch.bfloat16 if out_dtype == L.DTYPE_BF16 else torch.float32,
+                              device=A.device)
+        elif kind == L.EPI_QKV_ROPE:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+        else:
+            raise ValueError("this epilogue needs an explicit `out`")
+    e = L.GemmEpilogue()
+    e.kind, e.act, e.out_dtype, e.tokens_per_batch = kind, act, out_dtype, tokens_per_batch
+    e.bias, e.out = _p(bias), out.data_ptr()
+    e.ldo = out.stride(0) if kind != L.EPI_UNPATCHIFY else 0
+    e.gate, e.gate_batch_stride = _p(gate), gate_batch_stride
+    e.rope_cos, e.rope_sin, e.rope_cols = _p(rope_cos), _p(rope_sin), rope_cols
+    e.patch_len, e.t_out = patch_len, t_out
+    L.check(L.load().jat_gemm_bf16(_ctx(A), A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K,
+                                   C.byref(e), cta_pair, block_n, _stream(A.device)))
+    return out
+
+
+def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None):
+    _chk(qkv, torch.bfloat16, "qkv")
+    assert qkv.shape == (B * N, (Hq + 2 * Hkv) * head_dim)
+    if out is None:
+        out = torch.empty(B * N, Hq * head_dim, dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.load().jat_gqa_attention_fwd(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), B, N, Hq, Hkv, head_dim,
+                                           _stream(qkv.device)))
+    return out
+
+
+def cfg_euler_update(z, x_c, x_u, cfg_scale, t_dt, step):
+    """In-place fused CFG combine + x-pred->velocity + Euler update of z (all f32, same numel)."""
+    _chk(z, torch.float32, "z")
+    _chk(x_c, torch.float32, "x_c")
+    if x_u is not None:
+        _chk(x_u, torch.float32, "x_u")
+    _chk(t_dt, torch.float32, "t_dt")
+    L.check(L.load().jat_cfg_euler_update(_ctx(z), z.data_ptr(), x_c.data_ptr(), _p(x_u), float(cfg_scale),
+                                          t_dt.data_ptr(), step, z.numel(), _stream(z.device)))
+    return z

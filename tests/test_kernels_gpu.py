@@ -1,0 +1,264 @@
+"""Kernel-level parity tests (GPU): every C-ABI kernel against a plain torch fp32 restatement of the
+reference expression it replaces.  Tolerances are stated per test; bf16 outputs are compared after
+the same bf16 rounding of the operands, so what is measured is the kernel, not the quantisation."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from jat_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def L():
+    from jat_b200 import _lib
+    return _lib
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------- elementwise
+@pytest.mark.parametrize("cfg", [3.0, 1.0])
+@pytest.mark.parametrize("shape", [(2, 1024, 1378), (1, 1024, 86), (3, 7, 5)])
+def test_cfg_euler_update_bit_exact(ops, cfg, shape):
+    g = torch.Generator(device="cpu").manual_seed(0)
+    z = torch.randn(shape, generator=g).to(dev())
+    xc = torch.randn(shape, generator=g).to(dev())
+    xu = torch.randn(shape, generator=g).to(dev())
+    steps = 50
+    ts = torch.linspace(0.0, 1.0, steps + 1, device=dev())
+    t_dt = torch.stack([ts[:-1], ts[1:] - ts[:-1]], dim=1).contiguous()
+    for step in (0, 17, 49):
+        t, dt = ts[step], ts[step + 1] - ts[step]
+        # reference expression, infer_test_v3m2.py:164,175-176
+        x = xu + cfg * (xc - xu) if cfg != 1.0 else xc
+        want = z + (x - z) / (1 - t + 1e-5) * dt
+        got = ops.cfg_euler_update(z.clone(), xc, xu if cfg != 1.0 else None, cfg, t_dt, step)
+        assert torch.equal(got, want), (got - want).abs().max().item()
+
+
+def test_cfg_euler_update_direct_branch(ops):
+    z = torch.randn(4, 33, device=dev())
+    xc = torch.randn(4, 33, device=dev())
+    t_dt = torch.tensor([[0.9995, 0.0005]], device=dev())
+    got = ops.cfg_euler_update(z.clone(), xc, None, 1.0, t_dt, 0)
+    assert torch.equal(got, xc)  # t >= 0.999 -> z = x_pred (infer_test_v3m2.py:177-179)
+
+
+@pytest.mark.parametrize("norm_kind", [0, 1])
+@pytest.mark.parametrize("D", [512, 1024, 1280])
+@pytest.mark.parametrize("mode", ["per_batch", "shared", "none"])
+def test_adaln_norm_modulate(ops, norm_kind, D, mode):
+    torch.manual_seed(1)
+    B, N = 3, 45
+    M = B * N
+    x = (torch.randn(M, D, device=dev()) * 1.7 + 0.3)
+    mod = torch.randn(B, 6 * D, device=dev()) * 0.5
+    w = torch.rand(D, device=dev()) + 0.5 if norm_kind == 1 else None
+    if norm_kind == 0:
+        xh = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    else:
+        xh = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    if mode == "none":
+        want = xh
+        got = ops.adaln_norm_modulate(x, None, None, 0, w, norm_kind, 1e-6, N)
+    else:
+        stride = 6 * D if mode == "per_batch" else 0
+        shift, scale = mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D]
+        if mode == "shared":
+            sh, sc = shift[:1].expand(B, D), scale[:1].expand(B, D)
+        else:
+            sh, sc = shift, scale
+        want = (xh.view(B, N, D) * (1 + sc.unsqueeze(1)) + sh.unsqueeze(1)).view(M, D)
+        got = ops.adaln_norm_modulate(x, shift, scale, stride, w, norm_kind, 1e-6, N)
+    err = (got.float() - want).abs().max().item()
+    # bf16 output rounding: half ulp = 2^-9 relative
+    assert err <= 2 ** -8 * want.abs().max().item() + 1e-5, err
+    assert rel_l2(got.float(), want) < 3e-3
+
+
+@pytest.mark.parametrize("T", [1378, 86, 516, 7])
+def test_patchify_cast(ops, T):
+    torch.manual_seed(2)
+    B, Cc, P = 4, 64, 4
+    xt = torch.randn(2, Cc, T, device=dev())      # xt_batch = 2 -> rows b read x_t[b % 2]
+    cond = torch.randn(2, Cc, T, device=dev())    # cond_batch = 2 -> b >= 2 read zeros
+    got = ops.patchify_cast(xt, cond, B)
+    pad = (P - T % P) % P
+    xt4 = torch.cat([xt, xt], 0)
+    c4 = torch.cat([cond, torch.zeros_like(cond)], 0)
+    xin = torch.nn.functional.pad(torch.cat([xt4, c4], dim=1), (0, pad))  # jat_audiosr_v2.py:411-421
+    N = xin.shape[-1] // P
+    want = xin.reshape(B, 2 * Cc, N, P).permute(0, 2, 1, 3).reshape(B * N, 2 * Cc * P)  # :225-227
+    assert torch.equal(got, want.to(torch.bfloat16))
+    got0 = ops.patchify_cast(xt, None, 2)
+    assert torch.equal(got0[:, Cc * P:], torch.zeros_like(got0[:, Cc * P:]))
+
+
+def test_timestep_features(ops):
+    t = torch.tensor([0.0, 0.13, 0.5, 0.98, 1.0], device=dev())
+    D = 1280
+    half = D // 2
+    k = math.log(10000) / (half - 1)
+    f = torch.exp(torch.arange(half, device=dev()) * -k)
+    e = t[:, None] * f[None, :]
+    want = torch.cat([e.sin(), e.cos()], -1)  # jat_audiosr_v2.py:185-189
+    got = ops.timestep_features(t, D)
+    assert (got.float() - want).abs().max().item() <= 2 ** -8
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def _ab(M, N, K, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev()).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * (1.0 / math.sqrt(K))).to(dev()).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(dev())
+    return A, W, bias
+
+
+GEMM_CFGS = [pytest.param(0, 256, id="cg1n256"), pytest.param(0, 128, id="cg1n128"),
+             pytest.param(1, 256, id="cg2n256"), pytest.param(1, 128, id="cg2n128")]
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 1280), (1000, 1280, 512), (56, 7680, 1280)])
+def test_gemm_bias_f32(ops, L, cta_pair, block_n, M, N, K):
+    A, W, bias = _ab(M, N, K)
+    want = A.float() @ W.float().t() + bias
+    got = ops.gemm(A, W, bias=bias, out_dtype=L.DTYPE_F32, cta_pair=cta_pair, block_n=block_n)
+    err = (got - want).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+    assert rel_l2(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_bias_act_bf16(ops, L, cta_pair, block_n, act):
+    M, N, K = 345 * 2, 1024, 256
+    A, W, bias = _ab(M, N, K, seed=3)
+    y = A.float() @ W.float().t() + bias
+    want = [y, torch.nn.functional.gelu(y), torch.nn.functional.silu(y)][act]
+    got = ops.gemm(A, W, bias=bias, act=act, out_dtype=L.DTYPE_BF16, cta_pair=cta_pair, block_n=block_n)
+    assert (got.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-3
+    assert rel_l2(got.float(), want) < 4e-3
+
+
+def _rope_tables(max_pos=4096, dim=64):
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))  # jat_audiosr_v2.py:60
+    freqs = torch.outer(torch.arange(max_pos).float(), inv_freq)
+    emb = torch.cat([freqs, freqs], -1)
+    return emb.cos().to(dev()).contiguous(), emb.sin().to(dev()).contiguous()
+
+
+def _rope_ref(x, cos, sin):
+    # x [B, N, H, 64]; jat_audiosr_v2.py:70-91
+    N = x.shape[1]
+    x1, x2 = x[..., :32], x[..., 32:]
+    rot = torch.cat([-x2, x1], -1)
+    return x * cos[:N].unsqueeze(0).unsqueeze(2) + rot * sin[:N].unsqueeze(0).unsqueeze(2)
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+def test_gemm_qkv_rope(ops, L, cta_pair, block_n):
+    B, N, D, Hq, Hkv = 3, 129, 1280, 20, 4
+    M, NQ = B * N, (Hq + 2 * Hkv) * 64
+    A, W, _ = _ab(M, NQ, D, seed=4)
+    cos, sin = _rope_tables()
+    y = (A.float() @ W.float().t()).view(B, N, Hq + 2 * Hkv, 64)
+    want = torch.cat([_rope_ref(y[:, :, :Hq + Hkv], cos, sin), y[:, :, Hq + Hkv:]], 2).reshape(M, NQ)
+    got = ops.gemm(A, W, kind=L.EPI_QKV_ROPE, tokens_per_batch=N, rope_cos=cos, rope_sin=sin,
+                   rope_cols=(Hq + Hkv) * 64, cta_pair=cta_pair, block_n=block_n)
+    assert (got.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-3
+    assert rel_l2(got.float(), want) < 4e-3
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("with_bias", [False, True])
+@pytest.mark.parametrize("stride_mode", ["per_batch", "shared"])
+def test_gemm_gate_residual(ops, L, cta_pair, block_n, with_bias, stride_mode):
+    B, N, D, K = 3, 120, 1280, 512
+    M = B * N
+    A, W, bias = _ab(M, D, K, seed=5)
+    x0 = torch.randn(M, D, device=dev())
+    mod = torch.randn(B, 6 * D, device=dev())
+    gate = mod[:, 2 * D:3 * D]
+    gb = gate if stride_mode == "per_batch" else gate[:1].expand(B, D)
+    y = A.float() @ W.float().t() + (bias if with_bias else 0.0)
+    want = x0 + (gb.unsqueeze(1) * y.view(B, N, D)).view(M, D)  # jat_audiosr_v2.py:281,287
+    x = x0.clone()
+    ops.gemm(A, W, kind=L.EPI_GATE_RESIDUAL, out=x, bias=bias if with_bias else None, gate=gate,
+             gate_batch_stride=6 * D if stride_mode == "per_batch" else 0, tokens_per_batch=N,
+             cta_pair=cta_pair, block_n=block_n)
+    assert (x - want).abs().max().item() < 5e-3
+    assert rel_l2(x, want) < 1e-4
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("T", [1378, 516, 86, 85])
+def test_gemm_unpatchify(ops, L, cta_pair, block_n, T):
+    B, Cc, P, K = 2, 256, 4, 256
+    N = (T + P - 1) // P
+    M = B * N
+    A, W, bias = _ab(M, Cc * P, K, seed=6)
+    y = A.float() @ W.float().t() + bias
+    want = y.view(B, N, Cc, P).permute(0, 2, 1, 3).reshape(B, Cc, N * P)[:, :, :T]  # jat_audiosr_v2.py:383-397
+    out = torch.full((B, Cc, T), float("nan"), device=dev())
+    ops.gemm(A, W, kind=L.EPI_UNPATCHIFY, out=out, bias=bias, tokens_per_batch=N, patch_len=P, t_out=T,
+             cta_pair=cta_pair, block_n=block_n)
+    assert torch.isfinite(out).all()
+    assert (out - want).abs().max().item() < 5e-3
+    assert rel_l2(out, want) < 1e-4
+
+
+def test_gemm_headline_shape_tail(ops, L):
+    """M = 19320 = 150*128 + 120: the ragged last M tile of the headline config."""
+    M, N, K = 19320, 1280, 1280
+    A, W, bias = _ab(M, N, K, seed=7)
+    got = ops.gemm(A, W, bias=bias, out_dtype=L.DTYPE_F32)
+    for lo, hi in [(0, 256), (9000, 9300), (19200, 19320)]:
+        want = A[lo:hi].float() @ W.float().t() + bias
+        assert rel_l2(got[lo:hi], want) < 1e-4
+
+
+def test_gemm_rejects_bad_shapes(ops, L):
+    A = torch.zeros(8, 100, dtype=torch.bfloat16, device=dev())
+    W = torch.zeros(128, 100, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(L.JatError):
+        ops.gemm(A, W)
+
+
+# ------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 16, 4), (2, 256, 4, 4), (1, 352, 5, 1)])
+def test_gqa_attention(ops, B, N, Hq, Hkv):
+    torch.manual_seed(8)
+    hd = 64
+    qkv = (torch.randn(B * N, (Hq + 2 * Hkv) * hd, device=dev()) * 1.5).to(torch.bfloat16)
+    got = ops.gqa_attention_fwd(qkv, B, N, Hq, Hkv)
+    f = qkv.float().view(B, N, Hq + 2 * Hkv, hd)
+    Q, K, V = f[:, :, :Hq], f[:, :, Hq:Hq + Hkv], f[:, :, Hq + Hkv:]
+    G = Hq // Hkv
+    K = K.repeat_interleave(G, dim=2)  # jat_audiosr_v2.py:147-148
+    V = V.repeat_interleave(G, dim=2)
+    s = torch.matmul(Q.transpose(1, 2), K.transpose(1, 2).transpose(-2, -1)) / math.sqrt(hd)
+    want = torch.matmul(torch.softmax(s, -1), V.transpose(1, 2)).transpose(1, 2).reshape(B * N, Hq * hd)
+    err = (got.float() - want).abs().max().item()
+    assert err < 2e-2 * max(1.0, want.abs().max().item()), err  # P is rounded to bf16 before P.V
+    assert rel_l2(got.float(), want) < 8e-3
+
+
+def test_gqa_attention_rejects_long(ops, L):
+    qkv = torch.zeros(400, 3 * 64, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(L.JatError):
+        ops.gqa_attention_fwd(qkv, 1, 400, 1, 1)
