@@ -205,6 +205,16 @@ int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit
 /* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
 int64_t jat_launch_count(const jat_ctx* ctx);
 
+/* Default GEMM tile configuration used when a call passes cta_pair < 0 / block_n == 0. */
+int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
+
+/* Per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline of
+ * each kernel class inside a real step).  Between begin and end every launch is bracketed by an event
+ * pair; `jat_profile_end` synchronises the device and returns, per kernel class, the summed duration
+ * and the launch count.  Not for use during CUDA-graph capture. Returns the number of classes filled. */
+int jat_profile_begin(jat_ctx* ctx);
+int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

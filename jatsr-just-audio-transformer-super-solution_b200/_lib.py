@@ -99,6 +99,8 @@ SIGNATURES = {
     "jat_sm_count": (_i, [_vp]),
     "jat_launch_count": (_i64, [_vp]),
     "jat_set_gemm_config": (_i, [_vp, _i, _i]),
+    "jat_profile_begin": (_i, [_vp]),
+    "jat_profile_end": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "jat_adaln_norm_modulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _i, _i, _i, _vp]),
     "jat_patchify_cast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "jat_timestep_features": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -159,3 +161,19 @@ def context(device_index: int) -> int:
             h = out.value
             _ctx[device_index] = h
     return h
+
+
+def profile_begin(device_index: int) -> None:
+    check(load().jat_profile_begin(context(device_index)))
+
+
+def profile_end(device_index: int) -> dict:
+    """{kernel class: (total_ms, launches)} since profile_begin (synchronises the device)."""
+    n = 16
+    names = (C.c_char_p * n)()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    got = load().jat_profile_end(context(device_index), n, names, ms, cnt)
+    if got < 0:
+        check(got)
+    return {names[i].decode(): (ms[i], cnt[i]) for i in range(got) if cnt[i] > 0}

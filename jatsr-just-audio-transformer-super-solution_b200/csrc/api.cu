@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <new>
+#include <vector>
 
 #include "../../include/jat_b200.h"
 #include "attention_gqa.cuh"
@@ -28,7 +29,18 @@ struct jat_ctx {
     std::atomic<long long> launches;
     int gemm_cta_pair;  // default tile configuration (overridable per call)
     int gemm_block_n;
+    // optional per-launch CUDA-event profiling (jat_profile_*): one (start, stop) pair per launch
+    bool profiling;
+    std::vector<cudaEvent_t> ev_start, ev_stop;
+    std::vector<int> ev_tag;
+    size_t ev_used;
+    cudaStream_t cur_stream;
 };
+
+static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
+                                          "adaln_norm_modulate", "patchify_cast", "timestep_features",
+                                          "cfg_euler_update", "gqa_attention_fwd"};
+enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_COUNT = 9 };
 
 static thread_local char g_err[512] = "";
 
@@ -78,10 +90,18 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->launches.store(0);
     c->gemm_cta_pair = 0;
     c->gemm_block_n = 0;
+    c->profiling = false;
+    c->ev_used = 0;
+    c->cur_stream = nullptr;
     *out = c;
     return 0;
 }
-extern "C" void jat_destroy(jat_ctx* ctx) { delete ctx; }
+extern "C" void jat_destroy(jat_ctx* ctx) {
+    if (!ctx) return;
+    for (cudaEvent_t e : ctx->ev_start) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_stop) cudaEventDestroy(e);
+    delete ctx;
+}
 extern "C" int jat_sm_count(const jat_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" int64_t jat_launch_count(const jat_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
@@ -92,14 +112,55 @@ extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
     return 0;
 }
 
+// Profiling mode: bracket the launch with a CUDA-event pair on the launching stream.
+static void pre_launch(jat_ctx* ctx, int tag, cudaStream_t s) {
+    if (!ctx->profiling) return;
+    if (ctx->ev_used == ctx->ev_start.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { ctx->profiling = false; return; }
+        ctx->ev_start.push_back(a);
+        ctx->ev_stop.push_back(b);
+        ctx->ev_tag.push_back(tag);
+    }
+    ctx->ev_tag[ctx->ev_used] = tag;
+    ctx->cur_stream = s;
+    cudaEventRecord(ctx->ev_start[ctx->ev_used], s);
+}
 static int post_launch(jat_ctx* ctx, const char* name) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "launch %s: %s", name, cudaGetErrorString(e));
         return (int)e;
     }
+    if (ctx->profiling) {
+        cudaEventRecord(ctx->ev_stop[ctx->ev_used], ctx->cur_stream);
+        ctx->ev_used++;
+    }
     ctx->launches.fetch_add(1);
     return 0;
+}
+
+extern "C" int jat_profile_begin(jat_ctx* ctx) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    ctx->profiling = true;
+    ctx->ev_used = 0;
+    return 0;
+}
+// Synchronises the device, then fills per-kernel-class totals; returns the number of classes.
+extern "C" int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts) {
+    if (!ctx || !names || !total_ms || !counts) return fail(JAT_ERR_BAD_ARG, "jat_profile_end: null argument");
+    ctx->profiling = false;
+    JAT_CUDA(cudaDeviceSynchronize());
+    const int n = max_tags < TAG_COUNT ? max_tags : TAG_COUNT;
+    for (int i = 0; i < n; ++i) { names[i] = kKernelTags[i]; total_ms[i] = 0.0; counts[i] = 0; }
+    for (size_t i = 0; i < ctx->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_start[i], ctx->ev_stop[i]) != cudaSuccess) continue;
+        const int t = ctx->ev_tag[i];
+        if (t < n) { total_ms[t] += ms; counts[t]++; }
+    }
+    ctx->ev_used = 0;
+    return n;
 }
 
 // 2D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch ld elements; box = box_rows x 64
@@ -144,6 +205,7 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    pre_launch(ctx, TAG_GEMM0 + EPI, s);
     JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
     return post_launch(ctx, "gemm_tcgen05");
 }
@@ -243,6 +305,7 @@ static int launch_adaln(jat_ctx* ctx, const float* x, __nv_bfloat16* out, const 
     const int nvec = D / 4;
     const int nv = (nvec + 31) / 32;
     dim3 grid((M + ADALN_WARPS - 1) / ADALN_WARPS), block(ADALN_WARPS * 32);
+    pre_launch(ctx, TAG_ADALN, s);
 #define JAT_ADALN_CASE(NV)                                                                                       \
     adaln_norm_modulate_kernel<NV, NORM><<<grid, block, 0, s>>>(x, out, shift, scale, bstride, weight, eps, M, D, ntok)
     if (nv <= 4) JAT_ADALN_CASE(4);
@@ -285,6 +348,7 @@ extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, c
         return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: need C %% 32 == 0, 0 < B <= 65535");
     const int N = (T + P - 1) / P;
     dim3 grid((N + PATCH_TN - 1) / PATCH_TN, 2 * C / PATCH_TC, B);
+    pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
     patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, xt_batch, x_cond, cond_batch,
                                                                  (__nv_bfloat16*)out_bf16, C, T, N);
     return post_launch(ctx, "patchify_cast");
@@ -294,6 +358,7 @@ extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf1
     if (!ctx || !t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_timestep_features: null argument");
     if (B <= 0 || D < 4 || D % 2 != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_timestep_features: bad B/D");
     dim3 grid((D / 2 + 127) / 128, B);
+    pre_launch(ctx, TAG_TSTEP, (cudaStream_t)stream);
     timestep_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out_bf16, B, D);
     return post_launch(ctx, "timestep_features");
 }
@@ -305,6 +370,7 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
     long long want = (numel / 4 + 255) / 256;
     long long cap = (long long)ctx->sm_count * 8;
     int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    pre_launch(ctx, TAG_EULER, (cudaStream_t)stream);
     cfg_euler_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, x_c, x_u, cfg_scale, t_dt, step,
                                                                        (long long)numel);
     return post_launch(ctx, "cfg_euler_update");
@@ -338,6 +404,7 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, i
         configured = true;
     }
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
+    pre_launch(ctx, TAG_ATTN, (cudaStream_t)stream);
     gqa_attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, p);
     return post_launch(ctx, "gqa_attention_fwd");
 }

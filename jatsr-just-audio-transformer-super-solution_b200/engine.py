@@ -1,0 +1,180 @@
+"""Host-side engine behind the nn.Module facade: weight packing, workspaces and the launch plan.
+
+All device computation is done by libjat_b200.so through `jat_dit_modulation` /
+`jat_dit_forward_tokens` (see include/jat_b200.h); torch only owns the memory.
+
+HBM layout (M = B * N token rows, N = ceil(T / patch_len)):
+  weights   bf16, nn.Linear [out, in] row-major = K-major B operand of the tcgen05 GEMM;
+            q/k/v projections concatenated row-wise into one [(Hq+2Hkv)*64, D] matrix per block;
+            every block's adaLN_modulation.1 stacked into one [depth*6D, D] matrix (one GEMM for all
+            blocks' shift/scale/gate); biases / norm weights / RoPE tables f32.
+  patches   bf16 [M, 2*C*P]   pe_hid bf16 [M, bottleneck]   x f32 [M, D] (residual stream)
+  h         bf16 [M, D]       qkv   bf16 [M, (Hq+2Hkv)*64]  attn bf16 [M, D]   mlp_hid bf16 [M, 4D]
+  mod       f32 [Bt, depth*6D]  (Bt = batch for a plain forward, = num_steps for the sampler)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+class PackedWeights:
+    """bf16/f32 device copies of a model's parameters in the layout the C-ABI expects."""
+
+    def __init__(self, model, device):
+        self.device = device
+        self.versions = self._versions(model)
+        bf = lambda t: t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        D, depth = model.hidden_size, len(model.blocks)
+        keep = self.keep = {}
+        keep["pe_w1"], keep["pe_b1"] = bf(model.patch_embed.proj[0].weight), f32(model.patch_embed.proj[0].bias)
+        keep["pe_w2"], keep["pe_b2"] = bf(model.patch_embed.proj[2].weight), f32(model.patch_embed.proj[2].bias)
+        keep["te_w1"], keep["te_b1"] = bf(model.t_embedder[1].weight), f32(model.t_embedder[1].bias)
+        keep["te_w2"], keep["te_b2"] = bf(model.t_embedder[3].weight), f32(model.t_embedder[3].bias)
+        keep["ada_w"] = bf(torch.cat([b.adaLN_modulation[1].weight.detach() for b in model.blocks], 0))
+        keep["ada_b"] = f32(torch.cat([b.adaLN_modulation[1].bias.detach() for b in model.blocks], 0))
+        keep["wqkv"] = [bf(torch.cat([b.attn.q_proj.weight.detach(), b.attn.k_proj.weight.detach(),
+                                      b.attn.v_proj.weight.detach()], 0)) for b in model.blocks]
+        keep["wo"] = [bf(b.attn.out_proj.weight) for b in model.blocks]
+        keep["w1"] = [bf(b.mlp[0].weight) for b in model.blocks]
+        keep["b1"] = [f32(b.mlp[0].bias) for b in model.blocks]
+        keep["w2"] = [bf(b.mlp[3].weight) for b in model.blocks]
+        keep["b2"] = [f32(b.mlp[3].bias) for b in model.blocks]
+        rms = model.norm_kind == L.NORM_RMSNORM
+        if rms:
+            keep["n1"] = [f32(b.norm1.weight) for b in model.blocks]
+            keep["n2"] = [f32(b.norm2.weight) for b in model.blocks]
+            keep["nf"] = f32(model.final_layer[0].weight)
+        keep["final_w"], keep["final_b"] = bf(model.final_layer[1].weight), f32(model.final_layer[1].bias)
+        rope = model.blocks[0].attn.rope
+        keep["cos"], keep["sin"] = f32(rope.cos_cached), f32(rope.sin_cached)
+
+        self.arrays = {k: _ptr_array(keep[k]) for k in ("wqkv", "wo", "w1", "b1", "w2", "b2")}
+        if rms:
+            self.arrays["n1"], self.arrays["n2"] = _ptr_array(keep["n1"]), _ptr_array(keep["n2"])
+        w = self.struct = L.DitWeights()
+        attn0 = model.blocks[0].attn
+        w.hidden, w.depth = D, depth
+        w.n_q_heads, w.n_kv_heads, w.head_dim = attn0.num_q_heads, attn0.num_kv_heads, attn0.head_dim
+        w.mlp_hidden = model.blocks[0].mlp[0].out_features
+        w.bottleneck = model.patch_embed.proj[0].out_features
+        w.channels, w.patch_len = model.input_channels, model.patch_len
+        w.norm_kind, w.max_len, w.rope_max_pos = model.norm_kind, model.max_len, rope.max_seq_len
+        w.norm_eps = 1e-6
+        p = lambda t: t.data_ptr()
+        w.pe_w1, w.pe_b1, w.pe_w2, w.pe_b2 = p(keep["pe_w1"]), p(keep["pe_b1"]), p(keep["pe_w2"]), p(keep["pe_b2"])
+        w.te_w1, w.te_b1, w.te_w2, w.te_b2 = p(keep["te_w1"]), p(keep["te_b1"]), p(keep["te_w2"]), p(keep["te_b2"])
+        w.ada_w, w.ada_b = p(keep["ada_w"]), p(keep["ada_b"])
+        cast = lambda a: C.cast(a, C.POINTER(C.c_void_p))
+        w.wqkv, w.wo = cast(self.arrays["wqkv"]), cast(self.arrays["wo"])
+        w.w1, w.b1, w.w2, w.b2 = (cast(self.arrays[k]) for k in ("w1", "b1", "w2", "b2"))
+        if rms:
+            w.norm1_w, w.norm2_w, w.final_norm_w = cast(self.arrays["n1"]), cast(self.arrays["n2"]), p(keep["nf"])
+        w.final_w, w.final_b = p(keep["final_w"]), p(keep["final_b"])
+        w.rope_cos, w.rope_sin = p(keep["cos"]), p(keep["sin"])
+
+    @staticmethod
+    def _versions(model):
+        return tuple((id(p), p._version, p.device) for p in model.parameters())
+
+    def stale(self, model, device):
+        return device != self.device or self._versions(model) != self.versions
+
+
+class Workspace:
+    """Activation buffers for one (B, T, Bt) problem size."""
+
+    def __init__(self, model, B, T, Bt, device, keep_blocks=False):
+        w = model
+        D = w.hidden_size
+        P, Cc = w.patch_len, w.input_channels
+        N = (T + P - 1) // P
+        M = B * N
+        attn0 = w.blocks[0].attn
+        qkv = (attn0.num_q_heads + 2 * attn0.num_kv_heads) * attn0.head_dim
+        F = w.blocks[0].mlp[0].out_features
+        depth = len(w.blocks)
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=device)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.B, self.T, self.Bt, self.N, self.M = B, T, Bt, N, M
+        self.buf = dict(
+            patches=bf(M, 2 * Cc * P), pe_hid=bf(M, w.patch_embed.proj[0].out_features), x=f32(M, D), h=bf(M, D),
+            qkv=bf(M, qkv), attn=bf(M, D), mlp_hid=bf(M, F),
+            t_feat=bf(Bt, D), t_hid=bf(Bt, D), t_act=bf(Bt, D), mod=f32(Bt, depth * 6 * D),
+        )
+        self.block_out = f32(depth, M, D) if keep_blocks else None
+        s = self.struct = L.DitWorkspace()
+        for k, v in self.buf.items():
+            setattr(s, k, v.data_ptr())
+        s.block_out = self.block_out.data_ptr() if keep_blocks else None
+        self.mod = self.buf["mod"]
+
+
+class Engine:
+    """Per-model engine: caches packed weights and workspaces, issues the C-ABI calls."""
+
+    def __init__(self, model):
+        self.model = model
+        self.packed = None
+        self.workspaces = {}
+
+    def weights(self, device):
+        if self.packed is None or self.packed.stale(self.model, device):
+            self.packed = PackedWeights(self.model, device)
+        return self.packed
+
+    def workspace(self, B, T, Bt, device, keep_blocks=False):
+        key = (B, T, Bt, device, keep_blocks)
+        ws = self.workspaces.get(key)
+        if ws is None:
+            if len(self.workspaces) >= 4:
+                self.workspaces.clear()
+            ws = self.workspaces[key] = Workspace(self.model, B, T, Bt, device, keep_blocks)
+        return ws
+
+    @staticmethod
+    def _dev_index(device):
+        return device.index if device.index is not None else torch.cuda.current_device()
+
+    def modulation(self, ws, t):
+        """t f32 [Bt] (device) -> ws.mod [Bt, depth*6D]."""
+        dev = t.device
+        lib, ctx = L.load(), L.context(self._dev_index(dev))
+        pw = self.weights(dev)
+        L.check(lib.jat_dit_modulation(ctx, C.byref(pw.struct), C.byref(ws.struct), t.data_ptr(), t.shape[0],
+                                       torch.cuda.current_stream(dev).cuda_stream))
+        return ws.mod
+
+    def forward_tokens(self, ws, x_t, x_cond, B, mod, mod_batch_stride, out, cond_batch=None):
+        dev = x_t.device
+        lib, ctx = L.load(), L.context(self._dev_index(dev))
+        pw = self.weights(dev)
+        T = x_t.shape[-1]
+        cb = 0 if x_cond is None else (x_cond.shape[0] if cond_batch is None else cond_batch)
+        code = lib.jat_dit_forward_tokens(ctx, C.byref(pw.struct), C.byref(ws.struct), x_t.data_ptr(), x_t.shape[0],
+                                          0 if x_cond is None else x_cond.data_ptr(), cb, mod.data_ptr(),
+                                          mod_batch_stride, out.data_ptr(), B, T,
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        if code == L.ERR_SEQ_TOO_LONG:  # reference raises ValueError (jat_audiosr_v2.py:428-429)
+            raise ValueError(lib.jat_last_error().decode())
+        L.check(code)
+        return out
+
+    def forward(self, x_t, t, x_cond, keep_blocks=False):
+        """Plain model forward: per-sample t (jat_audiosr_v2.py:399-448)."""
+        B, Cc, T = x_t.shape
+        dev = x_t.device
+        ws = self.workspace(B, T, B, dev, keep_blocks)
+        self.modulation(ws, t)
+        out = torch.empty(B, Cc, T, dtype=torch.float32, device=dev)
+        self.forward_tokens(ws, x_t, x_cond, B, ws.mod, ws.mod.shape[1], out)
+        return (out, ws.block_out) if keep_blocks else out

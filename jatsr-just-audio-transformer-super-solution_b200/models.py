@@ -1,0 +1,178 @@
+"""Drop-in mirrors of the reference DiT modules, executing on the sm_100a C-ABI library.
+
+  JaT_AudioSR_V2  <->  reference src/models/jat_audiosr_v2.py:292 (LayerNorm, no affine)
+  JaT_AudioSR_V3  <->  reference src/models/jat_audiosr_v3.py:311 (RMSNorm with weight)
+
+Same constructor keywords (jat_audiosr_v2.py:297-308), same ``forward(x_t, t, x_cond)`` contract
+(:399-448), same ``state_dict`` keys / shapes / persistent RoPE buffers, and -- because parameters are
+created in the reference's order with the same initialisers -- the same random initial weights under
+the same ``torch.manual_seed``.  The nn.Module tree below is a parameter container only: the forward
+pass is one call into `Engine`, which enqueues hand-written CUDA kernels.  There is no PyTorch or CPU
+execution path; calling the model on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import Engine
+
+
+class TimeEmbedding(nn.Module):
+    """Parameter-free placeholder at t_embedder.0 (jat_audiosr_v2.py:170-190); computed by
+    `jat_timestep_features`."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+
+class RoPE(nn.Module):
+    """Persistent RoPE buffers with the reference's names and values (jat_audiosr_v2.py:50-68)."""
+
+    def __init__(self, dim, max_seq_len=4096, base=10000):
+        super().__init__()
+        self.dim, self.max_seq_len, self.base = dim, max_seq_len, base
+        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer("inv_freq", inv_freq)
+        freqs = torch.outer(torch.arange(max_seq_len).float(), inv_freq)
+        emb = torch.cat([freqs, freqs], dim=-1)
+        self.register_buffer("cos_cached", emb.cos())
+        self.register_buffer("sin_cached", emb.sin())
+
+
+class GroupedQueryAttention(nn.Module):
+    """q/k/v/out projections (no bias) + RoPE buffers (jat_audiosr_v2.py:94-125)."""
+
+    def __init__(self, hidden_size, num_q_heads, num_kv_heads, dropout=0.0):
+        super().__init__()
+        assert hidden_size % num_q_heads == 0, "hidden_size must be divisible by num_q_heads"
+        assert num_q_heads % num_kv_heads == 0, "num_q_heads must be divisible by num_kv_heads"
+        self.hidden_size, self.num_q_heads, self.num_kv_heads = hidden_size, num_q_heads, num_kv_heads
+        self.num_groups = num_q_heads // num_kv_heads
+        self.head_dim = hidden_size // num_q_heads
+        self.q_proj = nn.Linear(hidden_size, hidden_size, bias=False)
+        kv = num_kv_heads * self.head_dim
+        self.k_proj = nn.Linear(hidden_size, kv, bias=False)
+        self.v_proj = nn.Linear(hidden_size, kv, bias=False)
+        self.out_proj = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.dropout = nn.Dropout(dropout)
+        self.rope = RoPE(self.head_dim)
+
+
+class BottleneckPatchEmbed1D(nn.Module):
+    def __init__(self, patch_len, in_chans, embed_dim, bottleneck_dim):
+        super().__init__()
+        self.patch_len = patch_len
+        self.flatten_dim = patch_len * in_chans
+        self.proj = nn.Sequential(nn.Linear(self.flatten_dim, bottleneck_dim), nn.GELU(),
+                                  nn.Linear(bottleneck_dim, embed_dim))
+
+
+class DropPath(nn.Module):
+    def __init__(self, drop_prob=0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+
+class DiTBlock_GQA(nn.Module):
+    """adaLN-Zero block parameters (jat_audiosr_v2.py:234-263 / jat_audiosr_v3.py:252-282)."""
+
+    def __init__(self, hidden_size, num_q_heads, num_kv_heads, mlp_ratio=4.0, dropout=0.1, drop_path=0.0,
+                 rms_norm=False):
+        super().__init__()
+        mk = (lambda: nn.RMSNorm(hidden_size, eps=1e-6)) if rms_norm else \
+            (lambda: nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6))
+        self.norm1 = mk()
+        self.attn = GroupedQueryAttention(hidden_size, num_q_heads, num_kv_heads, dropout=dropout)
+        self.norm2 = mk()
+        hid = int(hidden_size * mlp_ratio)
+        self.mlp = nn.Sequential(nn.Linear(hidden_size, hid), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hid, hidden_size), nn.Dropout(dropout))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+
+class _JaTBase(nn.Module):
+    norm_kind = L.NORM_LAYERNORM
+
+    def __init__(self, input_channels=1024, cond_channels=1024, patch_len=4, hidden_size=1024, depth=16,
+                 num_q_heads=16, num_kv_heads=4, bottleneck_dim=512, mlp_ratio=4.0, dropout=0.1,
+                 drop_path_rate=0.0):
+        super().__init__()
+        self.input_channels, self.cond_channels = input_channels, cond_channels
+        self.patch_len, self.hidden_size = patch_len, hidden_size
+        self.dropout_p, self.drop_path_rate = dropout, drop_path_rate
+        rms = self.norm_kind == L.NORM_RMSNORM
+        self.patch_embed = BottleneckPatchEmbed1D(patch_len, input_channels + cond_channels, hidden_size,
+                                                  bottleneck_dim)
+        self.max_len = 2048
+        self.t_embedder = nn.Sequential(TimeEmbedding(hidden_size), nn.Linear(hidden_size, hidden_size), nn.SiLU(),
+                                        nn.Linear(hidden_size, hidden_size))
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            DiTBlock_GQA(hidden_size, num_q_heads, num_kv_heads, mlp_ratio, dropout=dropout, drop_path=dpr[i],
+                         rms_norm=rms) for i in range(depth)])
+        fin_norm = nn.RMSNorm(hidden_size, eps=1e-6) if rms else \
+            nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.final_layer = nn.Sequential(fin_norm, nn.Linear(hidden_size, patch_len * input_channels))
+        self.initialize_weights()
+        object.__setattr__(self, "_engine", Engine(self))  # not a submodule / not in state_dict
+
+    def initialize_weights(self):
+        """adaLN-Zero: zero the modulation and final projections (jat_audiosr_v2.py:372-381)."""
+        for block in self.blocks:
+            nn.init.constant_(block.adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(block.adaLN_modulation[-1].bias, 0)
+        nn.init.constant_(self.final_layer[-1].weight, 0)
+        nn.init.constant_(self.final_layer[-1].bias, 0)
+
+    # ------------------------------------------------------------------------------------ forward
+    def _check_inputs(self, x_t, t, x_cond):
+        if not (x_t.is_cuda and x_cond.is_cuda and t.is_cuda):
+            raise RuntimeError("jat_b200 models run on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if x_t.dim() != 3 or x_t.shape != x_cond.shape or x_t.shape[1] != self.input_channels:
+            raise ValueError(f"expected x_t/x_cond [B, {self.input_channels}, T], got {tuple(x_t.shape)} / "
+                             f"{tuple(x_cond.shape)}")
+        if self.cond_channels != self.input_channels:
+            raise NotImplementedError("cond_channels != input_channels is not supported by the fused patchify")
+        if t.dim() != 1 or t.shape[0] != x_t.shape[0]:
+            raise ValueError("t must be [B]")
+        if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
+            raise NotImplementedError("train-mode Dropout/DropPath is not implemented by the CUDA path yet; "
+                                      "call model.eval()")
+        N = (x_t.shape[-1] + self.patch_len - 1) // self.patch_len
+        if N > self.max_len:
+            raise ValueError(f"Sequence length {N} exceeds max_len {self.max_len}")
+
+    def forward(self, x_t, t, x_cond):
+        """x_t, x_cond [B, C, T]; t [B] in [0, 1] -> x_pred [B, C, T] (jat_audiosr_v2.py:399-448)."""
+        self._check_inputs(x_t, t, x_cond)
+        out = self._engine.forward(x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous())
+        if torch.is_autocast_enabled():
+            out = out.to(torch.get_autocast_gpu_dtype())
+        return out
+
+    @torch.no_grad()
+    def forward_with_blocks(self, x_t, t, x_cond):
+        """Parity-test helper: (x_pred, per-block residual stream f32 [depth, B*N, D])."""
+        self._check_inputs(x_t, t, x_cond)
+        return self._engine.forward(x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous(),
+                                    keep_blocks=True)
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        if getattr(self, "_engine", None) is not None:
+            self._engine.packed = None  # .to()/.half()/... invalidates packed device copies
+        return r
+
+
+class JaT_AudioSR_V2(_JaTBase):
+    """LayerNorm variant (the class `train_ddp_v3mod2.py` trains)."""
+    norm_kind = L.NORM_LAYERNORM
+
+
+class JaT_AudioSR_V3(_JaTBase):
+    """RMSNorm variant (the class `infer_test_v3m2.py` / `train_ddp_v3m2.py` use)."""
+    norm_kind = L.NORM_RMSNORM

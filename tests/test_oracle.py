@@ -1,0 +1,124 @@
+"""CPU tests pinning the numpy oracle (oracle/dit_oracle.py) to the reference:
+  * against the committed golden fixtures (outputs of the reference modules, tests/golden/make_golden.py);
+  * directly against the reference modules when /root/reference is present (build container only).
+Tolerance: the oracle and the reference are both fp32 restatements of the same formulas; they differ
+only by summation order inside BLAS, so max-abs 2e-5 / rel-L2 1e-5 on O(1) activations."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import dit_oracle as O  # noqa: E402
+from tests._util import (have_reference, import_reference, load_golden, rel_l2, rerandomise_zero_init,  # noqa: E402
+                         state_dict_numpy)
+
+
+@pytest.mark.parametrize("tag", ["v2_layernorm", "v3_rmsnorm"])
+def test_oracle_forward_matches_golden(tag):
+    d, cfg, w = load_golden(tag)
+    out, blocks = O.dit_forward(w, d["x_t"], d["t"], d["cond"], num_q_heads=cfg["num_q_heads"],
+                                num_kv_heads=cfg["num_kv_heads"], patch_len=cfg["patch_len"], return_blocks=True)
+    assert out.shape == d["out"].shape
+    assert np.abs(d["out"]).max() > 0.1  # not the vacuous all-zero output of an un-randomised adaLN-Zero model
+    assert np.abs(out - d["out"]).max() < 2e-5
+    assert rel_l2(out, d["out"]) < 1e-5
+    for i, b in enumerate(blocks):
+        assert rel_l2(b, d["blocks"][i]) < 1e-5, i
+
+
+@pytest.mark.parametrize("tag", ["v2_layernorm", "v3_rmsnorm"])
+@pytest.mark.parametrize("name", ["cfg3", "cfg1"])
+def test_oracle_sampler_matches_golden(tag, name):
+    d, cfg, w = load_golden(tag)
+    z = O.flow_matching_sample(w, d["s_lr"], d[f"s_{name}_z0"], num_steps=int(d[f"s_{name}_steps"]),
+                               cfg_scale=float(d[f"s_{name}_cfg"]), num_q_heads=cfg["num_q_heads"],
+                               num_kv_heads=cfg["num_kv_heads"], patch_len=cfg["patch_len"])
+    assert np.abs(z - d[f"s_{name}_out"]).max() < 5e-5
+    assert rel_l2(z, d[f"s_{name}_out"]) < 1e-5
+
+
+def test_oracle_schedule_is_torch_linspace():
+    import torch
+    for n in (1, 2, 5, 25, 50, 100, 1000):
+        assert np.array_equal(O.sampler_schedule(n), torch.linspace(0.0, 1.0, n + 1).numpy())
+
+
+def test_oracle_euler_update_matches_torch_expression():
+    import torch
+    g = torch.Generator().manual_seed(0)
+    z, xc, xu = (torch.randn(3, 5, 7, generator=g) for _ in range(3))
+    ts = torch.linspace(0.0, 1.0, 51)
+    for i in (0, 13, 49):
+        t, dt = ts[i], ts[i + 1] - ts[i]
+        x = xu + 3.0 * (xc - xu)
+        want = z + (x - z) / (1 - t + 1e-5) * dt  # infer_test_v3m2.py:164,175-176
+        got = O.euler_cfg_update(z.numpy(), xc.numpy(), xu.numpy(), 3.0, t.numpy(), dt.numpy())
+        assert np.array_equal(got, want.numpy())
+
+
+def test_oracle_rejects_long_sequences():
+    _, cfg, w = load_golden("v2_layernorm")
+    x = np.zeros((1, cfg["input_channels"], 4 * 2049), np.float32)
+    with pytest.raises(ValueError):
+        O.dit_forward(w, x, np.zeros(1, np.float32), x, num_q_heads=cfg["num_q_heads"],
+                      num_kv_heads=cfg["num_kv_heads"])
+
+
+# ------------------------------------------------------------------ direct comparison with the reference
+REF_CASES = [
+    # (class idx, cfg, B, T)  -- BASELINE config C1 (v1 tiny, [1,1024,86]) and a GQA case with 2 KV groups
+    (0, dict(input_channels=1024, cond_channels=1024, patch_len=4, hidden_size=512, depth=12, num_q_heads=8,
+             num_kv_heads=4, bottleneck_dim=512), 1, 86),
+    (1, dict(input_channels=64, cond_channels=64, patch_len=4, hidden_size=256, depth=3, num_q_heads=4,
+             num_kv_heads=2, bottleneck_dim=64, mlp_ratio=2.0), 2, 517),
+    (0, dict(input_channels=64, cond_channels=64, patch_len=4, hidden_size=320, depth=2, num_q_heads=5,
+             num_kv_heads=1, bottleneck_dim=64), 2, 88),
+]
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("case", range(len(REF_CASES)))
+def test_oracle_matches_reference_module(case):
+    import torch
+    cls_idx, cfg, B, T = REF_CASES[case]
+    classes = import_reference()
+    torch.manual_seed(case)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = classes[cls_idx](**cfg).eval()
+    rerandomise_zero_init(model, seed=case + 1, bf16_exact=False)
+    g = torch.Generator().manual_seed(100 + case)
+    x_t = torch.randn(B, cfg["input_channels"], T, generator=g)
+    cond = torch.randn(B, cfg["input_channels"], T, generator=g)
+    t = torch.rand(B, generator=g)
+    with torch.no_grad():
+        want = model(x_t, t, cond).numpy()
+    got = O.dit_forward(state_dict_numpy(model), x_t.numpy(), t.numpy(), cond.numpy(),
+                        num_q_heads=cfg["num_q_heads"], num_kv_heads=cfg["num_kv_heads"])
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() < 3e-5
+    assert rel_l2(got, want) < 1e-5
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+def test_oracle_sampler_matches_reference_sampler():
+    import torch
+    cfg = dict(input_channels=64, cond_channels=64, patch_len=4, hidden_size=256, depth=2, num_q_heads=4,
+               num_kv_heads=2, bottleneck_dim=64, mlp_ratio=2.0)
+    V2, V3, ref_sample = import_reference()
+    torch.manual_seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = V3(**cfg).eval()
+    rerandomise_zero_init(model, seed=4, bf16_exact=False)
+    lr = torch.randn(2, 64, 86, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(77)
+    z0 = torch.randn(2, 64, 86)
+    torch.manual_seed(77)
+    want = ref_sample(model, lr, num_steps=6, cfg_scale=3.0, device="cpu", verbose=False).numpy()
+    got = O.flow_matching_sample(state_dict_numpy(model), lr.numpy(), z0.numpy(), num_steps=6, cfg_scale=3.0,
+                                 num_q_heads=4, num_kv_heads=2)
+    assert np.abs(got - want).max() < 1e-4
+    assert rel_l2(got, want) < 1e-5
