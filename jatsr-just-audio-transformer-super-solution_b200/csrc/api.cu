@@ -88,7 +88,7 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->encode = (PFN_encodeTiled)fn;
     c->launches.store(0);
-    c->gemm_cta_pair = 0;
+    c->gemm_cta_pair = 1;  // CTA pairs (cta_group::2) by default: half the B-operand smem traffic per SM
     c->gemm_block_n = 0;
     c->profiling = false;
     c->ev_used = 0;
@@ -163,18 +163,20 @@ extern "C" int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, d
     return n;
 }
 
-// 2D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch ld elements; box = box_rows x 64
-// columns (128 bytes), 128-byte swizzle, out-of-bounds elements read as zero.
+// 2D tensor map: `rows` x `cols` (cols contiguous), row pitch ld elements; box = box_rows x box_cols with
+// box_cols * elem_bytes == 128 bytes, 128-byte swizzle, out-of-bounds elements read as zero / not written.
 static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows) {
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0)
-        return fail(JAT_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a row pitch multiple of 8 elements");
+                     uint32_t box_rows, bool f32 = false) {
+    const uint64_t esz = f32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * esz) % 16 != 0)
+        return fail(JAT_ERR_BAD_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {ld * 2};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint64_t gstr[1] = {ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = ctx->encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                             const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(JAT_ERR_TENSORMAP, "cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu ld %llu box_rows %u",
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
@@ -183,7 +185,8 @@ static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t ro
 
 // ------------------------------------------------------------------------------------------------ GEMM
 template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
-static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                       const GemmParams& p, cudaStream_t s) {
     using Cfg = GemmCfg<BN, CG>;
     auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16>;
     static bool configured = false;  // per instantiation
@@ -206,31 +209,31 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     pre_launch(ctx, TAG_GEMM0 + EPI, s);
-    JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
     return post_launch(ctx, "gemm_tcgen05");
 }
 
 template <int BN, int CG>
-static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                             const jat_gemm_epilogue* e, cudaStream_t s) {
+static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                             const GemmParams& p, const jat_gemm_epilogue* e, cudaStream_t s) {
     switch (e->kind) {
         case JAT_EPI_BIAS_ACT:
             if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_F32)
-                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 0>(ctx, ta, tb, p, s);
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 0>(ctx, ta, tb, to, p, s);
             if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_BF16)
-                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 1>(ctx, ta, tb, p, s);
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 1>(ctx, ta, tb, to, p, s);
             if (e->act == JAT_ACT_GELU_ERF && e->out_dtype == JAT_DTYPE_BF16)
-                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_GELU, 1>(ctx, ta, tb, p, s);
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_GELU, 1>(ctx, ta, tb, to, p, s);
             if (e->act == JAT_ACT_SILU && e->out_dtype == JAT_DTYPE_BF16)
-                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_SILU, 1>(ctx, ta, tb, p, s);
+                return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_SILU, 1>(ctx, ta, tb, to, p, s);
             return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unsupported act/out_dtype combination (%d, %d)", e->act,
                         e->out_dtype);
         case JAT_EPI_QKV_ROPE:
-            return launch_gemm<BN, CG, EPI_QKV_ROPE, ACT_NONE, 1>(ctx, ta, tb, p, s);
+            return launch_gemm<BN, CG, EPI_QKV_ROPE, ACT_NONE, 1>(ctx, ta, tb, to, p, s);
         case JAT_EPI_GATE_RESIDUAL:
-            return launch_gemm<BN, CG, EPI_GATE_RESIDUAL, ACT_NONE, 0>(ctx, ta, tb, p, s);
+            return launch_gemm<BN, CG, EPI_GATE_RESIDUAL, ACT_NONE, 0>(ctx, ta, tb, to, p, s);
         case JAT_EPI_UNPATCHIFY:
-            return launch_gemm<BN, CG, EPI_UNPATCHIFY, ACT_NONE, 0>(ctx, ta, tb, p, s);
+            return launch_gemm<BN, CG, EPI_UNPATCHIFY, ACT_NONE, 0>(ctx, ta, tb, to, p, s);
     }
     return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
 }
@@ -286,16 +289,23 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
             return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
     }
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to;
     JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
     JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg)));
+    if (e->kind == JAT_EPI_UNPATCHIFY) {
+        to = ta;  // unused by that epilogue
+    } else {
+        // epilogue slabs: 32 rows x 128 bytes, stored (or reduce-added) by the TMA unit; rows >= M are clipped
+        const bool out_f32 = e->kind == JAT_EPI_GATE_RESIDUAL || (e->kind == JAT_EPI_BIAS_ACT && e->out_dtype == JAT_DTYPE_F32);
+        JAT_TRY(make_tmap(ctx, &to, e->out, (uint64_t)M, (uint64_t)N, (uint64_t)e->ldo, 32, out_f32));
+    }
     cudaStream_t s = (cudaStream_t)stream;
     if (block_n == 256) {
-        if (cg == 1) return dispatch_gemm_epi<256, 1>(ctx, ta, tb, p, e, s);
-        return dispatch_gemm_epi<256, 2>(ctx, ta, tb, p, e, s);
+        if (cg == 1) return dispatch_gemm_epi<256, 1>(ctx, ta, tb, to, p, e, s);
+        return dispatch_gemm_epi<256, 2>(ctx, ta, tb, to, p, e, s);
     }
-    if (cg == 1) return dispatch_gemm_epi<128, 1>(ctx, ta, tb, p, e, s);
-    return dispatch_gemm_epi<128, 2>(ctx, ta, tb, p, e, s);
+    if (cg == 1) return dispatch_gemm_epi<128, 1>(ctx, ta, tb, to, p, e, s);
+    return dispatch_gemm_epi<128, 2>(ctx, ta, tb, to, p, e, s);
 }
 
 // ------------------------------------------------------------------------------------------------ AdaLN
@@ -377,36 +387,47 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
 }
 
 // ------------------------------------------------------------------------------------------------ attention
+template <int NKH>
+static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv, uint64_t rows, uint64_t cols,
+                            const AttnParams& p, dim3 grid, cudaStream_t s) {
+    using Cfg = AttCfg<NKH>;
+    CUtensorMap tkv;
+    JAT_TRY(make_tmap(ctx, &tkv, qkv, rows, cols, cols, (uint32_t)NKH));
+    static bool configured = false;
+    if (!configured) {
+        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel<NKH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    pre_launch(ctx, TAG_ATTN, s);
+    gqa_attention_fwd_kernel<NKH><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tkv, p);
+    return post_launch(ctx, "gqa_attention_fwd");
+}
+
 extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, int B, int N, int Hq, int Hkv,
                                      int head_dim, void* stream) {
     if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
     if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: bad B/N/heads");
-    const int NK = (N + 15) / 16 * 16;
-    if (NK > ATT_MAX_NK)
+    if (N > ATT_MAX_NK)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: N = %d tokens > %d not supported by the single-pass kernel", N,
                     ATT_MAX_NK);
     AttnParams p = {};
-    p.B = B; p.N = N; p.NK = NK; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
-    if (NK <= 256) { p.kv_box_rows = NK; p.kv_boxes = 1; p.nA = NK; p.nB = 0; }
-    else { p.kv_box_rows = NK / 2; p.kv_boxes = 2; p.nA = NK / 2; p.nB = NK - p.nA; }
+    p.B = B; p.N = N; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
     p.out = (__nv_bfloat16*)out;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
-    CUtensorMap tq, tkv;
+    CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
-    JAT_TRY(make_tmap(ctx, &tkv, qkv, rows, cols, cols, (uint32_t)p.kv_box_rows));
-    static bool configured = false;
-    if (!configured) {
-        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      ATT_SMEM_BYTES));
-        configured = true;
-    }
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
-    pre_launch(ctx, TAG_ATTN, (cudaStream_t)stream);
-    gqa_attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, p);
-    return post_launch(ctx, "gqa_attention_fwd");
+    cudaStream_t s = (cudaStream_t)stream;
+    // key range padded to NK = 2*NKH columns (two softmax warpgroups); padded keys are masked in-kernel
+    if (N <= 64) return launch_attention<32>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (N <= 128) return launch_attention<64>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (N <= 192) return launch_attention<96>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (N <= 256) return launch_attention<128>(ctx, tq, qkv, rows, cols, p, grid, s);
+    return launch_attention<176>(ctx, tq, qkv, rows, cols, p, grid, s);
 }
 
 // ------------------------------------------------------------------------------------------------ DiT forward plan

@@ -86,6 +86,29 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* tmap, uin
         : "memory");
 }
 
+// 2D tile store smem -> global (bulk async-group completion). Out-of-bounds rows/cols are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// 2D tile reduce-add smem -> global: global[tile] += smem[tile], performed by the TMA unit in L2.
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -209,7 +232,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU() default) with erf from Abramowitz-Stegun
+// 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of the result), arranged for the epilogue's
+// issue budget: 12 FMA-pipe ops + 2 MUFU (rcp, ex2), no branches.
+//   u = |x| sqrt(log2 e / 2);  t = 1 / (1 + p' u);  q = 0.5 poly(t) 2^(-u^2) = 1 - Phi(|x|);
+//   gelu(x) = max(x, 0) - |x q|
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float u = fabsf(x) * 0.84932180028801904f;                 // sqrt(log2(e) / 2)
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27273748f, u, 1.0f)));  // p / sqrt(log2 e), p = 0.3275911
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+    float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    p = fmaf(t, p, 0.5f * 1.421413741f);
+    p = fmaf(t, p, 0.5f * -0.284496736f);
+    p = fmaf(t, p, 0.5f * 0.254829592f);
+    const float q = p * t * e;
+    return fmaxf(x, 0.0f) - fabsf(x * q);
+}
+__device__ __forceinline__ float gelu_erf_ref(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -12,9 +12,14 @@
 //   warp 1      MMA issuer (one lane): tcgen05.mma kind::f16, M = 128*CG, N = BN, K = 16, accumulators
 //               double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps tile i+1
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld (thread = one accumulator row, 32 columns at a time) -> fused
-//               math -> global stores.  Warpgroup 0 takes columns [0, BN/2), warpgroup 1 the rest.
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+//   warps 4-11  epilogue: tcgen05.ld (thread = one accumulator row) -> fused math in registers ->
+//               128B-swizzled shared-memory slab (32 rows x 128 B per warp, double-buffered) -> TMA store,
+//               or TMA reduce-add for the gated residual (x += gate * (acc + bias) is performed by the
+//               TMA unit in L2: the epilogue never reads x).  Warpgroup 0 takes columns [0, BN/2) of the
+//               tile, warpgroup 1 the rest.  The un-patchify epilogue stores directly (its [B,C,T] target
+//               is already coalesced across lanes).
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue),
+// bulk async-groups (epilogue smem slab <-> TMA store).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -43,6 +48,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_SLAB_BYTES = 32 * 128;  // one epilogue slab: 32 rows x 128 B (64 bf16 or 32 f32 columns)
 
 template <int BN, int CG>
 struct GemmCfg {
@@ -50,10 +56,12 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES;  // 64 KB
+    static constexpr int STAGES_RAW = (160 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
 };
 
 template <int ACT>
@@ -63,14 +71,17 @@ __device__ __forceinline__ float apply_act(float v) {
     return v;
 }
 
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// 16-byte chunk `chunk` (0..7) of row `lane` inside a 128B-swizzled 32-row slab
+__device__ __forceinline__ void st_slab_chunk(uint32_t slab_row_addr, int lane, int chunk, uint32_t a, uint32_t b,
+                                              uint32_t c, uint32_t d) {
+    const uint32_t addr = slab_row_addr + (uint32_t)(((chunk ^ (lane & 7)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
 
@@ -78,8 +89,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // 128B-swizzled tiles need a 1024-byte aligned base (the swizzle is a function of address bits 4..9).
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
 
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* bar_empty = bar_full + STAGES;
     uint64_t* bar_tmem_full = bar_empty + STAGES;
     uint64_t* bar_tmem_empty = bar_tmem_full + 2;
@@ -94,6 +106,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if constexpr (EPI != EPI_UNPATCHIFY) tma_prefetch_desc(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -187,60 +200,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int wg = (warp - 4) >> 2;  // column half
         const int row_in_tile = quad * 32 + lane;
         constexpr int HALF = BN / 2;
+        uint8_t* my_stage = staging + (warp - 4) * 2 * GEMM_SLAB_BYTES;
+        const uint32_t slab_row[2] = {smem_u32(my_stage) + (uint32_t)lane * 128u,
+                                      smem_u32(my_stage + GEMM_SLAB_BYTES) + (uint32_t)lane * 128u};
+        int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-            const int m = (m_blk * CG + (int)cta_rank) * GEMM_BM + row_in_tile;
+            const int row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM + quad * 32;  // first row of this warp's slab
+            const int m = row0 + lane;
             const bool row_ok = m < p.M;
             const int n_base = n_blk * BN + wg * HALF;
             mbar_wait(&bar_tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + wg * HALF);
 
-            if constexpr (EPI == EPI_BIAS_ACT) {
+            if constexpr (EPI == EPI_BIAS_ACT && OUT_BF16) {
 #pragma unroll 1
-                for (int c = 0; c < HALF / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    const int n0 = n_base + c * 32;
-                    float f[32];
+                for (int sl = 0; sl < HALF / 64; ++sl) {  // slab = 64 bf16 columns
+                    const int n0 = n_base + sl * 64;
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                        f[j + 0] = apply_act<ACT>(__uint_as_float(v[j + 0]) + b4.x);
-                        f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
-                        f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
-                        f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
-                    }
-                    if (row_ok) {
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo + n0;
+                    for (int hx = 0; hx < 2; ++hx) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + sl * 64 + hx * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8)
-                                st_global_v4(o + j, pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                             pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-                        } else {
-                            float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n0;
+                        for (int j = 0; j < 32; j += 8) {
+                            float f[8];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            for (int q = 0; q < 8; q += 4) {
+                                const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hx * 32 + j + q))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                                f[q + 0] = apply_act<ACT>(__uint_as_float(v[j + q + 0]) + b4.x);
+                                f[q + 1] = apply_act<ACT>(__uint_as_float(v[j + q + 1]) + b4.y);
+                                f[q + 2] = apply_act<ACT>(__uint_as_float(v[j + q + 2]) + b4.z);
+                                f[q + 3] = apply_act<ACT>(__uint_as_float(v[j + q + 3]) + b4.w);
+                            }
+                            st_slab_chunk(slab_row[buf], lane, hx * 4 + j / 8, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                                          pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < p.M) tma_store_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
+                        tma_store_commit();
+                    }
+                    buf ^= 1;
+                }
+            } else if constexpr (EPI == EPI_BIAS_ACT || EPI == EPI_GATE_RESIDUAL) {
+                // f32 slabs of 32 columns.  GATE_RESIDUAL: slab = gate * (acc + bias), TMA-reduce-added into x.
+                const float* grow = nullptr;
+                if constexpr (EPI == EPI_GATE_RESIDUAL)
+                    grow = p.gate + (long long)(row_ok ? (m / p.tokens_per_batch) : 0) * p.gate_bstride;
+#pragma unroll 1
+                for (int sl = 0; sl < HALF / 32; ++sl) {
+                    const int n0 = n_base + sl * 32;
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + sl * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
+                              r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
+                        if constexpr (EPI == EPI_GATE_RESIDUAL) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
+                            r0 *= g4.x; r1 *= g4.y; r2 *= g4.z; r3 *= g4.w;
+                        } else {
+                            r0 = apply_act<ACT>(r0); r1 = apply_act<ACT>(r1); r2 = apply_act<ACT>(r2); r3 = apply_act<ACT>(r3);
+                        }
+                        st_slab_chunk(slab_row[buf], lane, j / 4, __float_as_uint(r0), __float_as_uint(r1),
+                                      __float_as_uint(r2), __float_as_uint(r3));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < p.M) {
+                            if constexpr (EPI == EPI_GATE_RESIDUAL)
+                                tma_reduce_add_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
+                            else
+                                tma_store_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
+                        }
+                        tma_store_commit();
+                    }
+                    buf ^= 1;
                 }
             } else if constexpr (EPI == EPI_QKV_ROPE) {
-                // 64-wide heads; rotate_half pairs column j with j+32 (jat_audiosr_v2.py:70-91).
+                // slab = one 64-wide head; rotate_half pairs column j with j+32 (jat_audiosr_v2.py:70-91).
                 const int pos = row_ok ? (m % p.tokens_per_batch) : 0;
                 const float* cosr = p.rope_cos + (long long)pos * 64;
                 const float* sinr = p.rope_sin + (long long)pos * 64;
-                __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo;
 #pragma unroll 1
                 for (int hh = 0; hh < HALF / 64; ++hh) {
                     const int n0 = n_base + hh * 64;
                     const bool rot = n0 < p.rope_cols;
-#pragma unroll 1
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+#pragma unroll
                     for (int s = 0; s < 2; ++s) {
                         uint32_t lo[16], hi[16];
                         tmem_ld_32x16(taddr + hh * 64 + s * 16, lo);
@@ -262,43 +325,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 oh[j + q] = b * cc[q] + a * ss[q];
                             }
                         }
-                        if (row_ok) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 8) {
-                                st_global_v4(orow + n0 + s * 16 + j, pack_bf16(ol[j], ol[j + 1]),
-                                             pack_bf16(ol[j + 2], ol[j + 3]), pack_bf16(ol[j + 4], ol[j + 5]),
-                                             pack_bf16(ol[j + 6], ol[j + 7]));
-                                st_global_v4(orow + n0 + 32 + s * 16 + j, pack_bf16(oh[j], oh[j + 1]),
-                                             pack_bf16(oh[j + 2], oh[j + 3]), pack_bf16(oh[j + 4], oh[j + 5]),
-                                             pack_bf16(oh[j + 6], oh[j + 7]));
-                            }
+                        for (int c = 0; c < 2; ++c) {
+                            st_slab_chunk(slab_row[buf], lane, s * 2 + c, pack_bf16(ol[c * 8 + 0], ol[c * 8 + 1]),
+                                          pack_bf16(ol[c * 8 + 2], ol[c * 8 + 3]), pack_bf16(ol[c * 8 + 4], ol[c * 8 + 5]),
+                                          pack_bf16(ol[c * 8 + 6], ol[c * 8 + 7]));
+                            st_slab_chunk(slab_row[buf], lane, 4 + s * 2 + c, pack_bf16(oh[c * 8 + 0], oh[c * 8 + 1]),
+                                          pack_bf16(oh[c * 8 + 2], oh[c * 8 + 3]), pack_bf16(oh[c * 8 + 4], oh[c * 8 + 5]),
+                                          pack_bf16(oh[c * 8 + 6], oh[c * 8 + 7]));
                         }
                     }
-                }
-            } else if constexpr (EPI == EPI_GATE_RESIDUAL) {
-                const int b = row_ok ? (m / p.tokens_per_batch) : 0;
-                const float* grow = p.gate + (long long)b * p.gate_bstride;
-                float* xrow = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo;
-#pragma unroll 1
-                for (int c = 0; c < HALF / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    const int n0 = n_base + c * 32;
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
-                            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                            float4 x4 = *reinterpret_cast<const float4*>(xrow + n0 + j);
-                            x4.x += g4.x * (__uint_as_float(v[j + 0]) + b4.x);
-                            x4.y += g4.y * (__uint_as_float(v[j + 1]) + b4.y);
-                            x4.z += g4.z * (__uint_as_float(v[j + 2]) + b4.z);
-                            x4.w += g4.w * (__uint_as_float(v[j + 3]) + b4.w);
-                            *reinterpret_cast<float4*>(xrow + n0 + j) = x4;
-                        }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < p.M) tma_store_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
+                        tma_store_commit();
                     }
+                    buf ^= 1;
                 }
             } else {  // EPI_UNPATCHIFY, patch_len 4: column = c*4 + p -> out[b, c, n*4 + p]
                 const int b = row_ok ? (m / p.tokens_per_batch) : 0;
@@ -335,7 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
 
-            // accumulator stage drained -> hand it back to the MMA issuer
+            // all TMEM reads of this accumulator stage are done -> hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -344,6 +387,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if ((as ^= 1) == 0) aphase ^= 1;
         }
+        if (lane == 0) tma_store_wait_all<0>();  // slabs must stay valid until the TMA unit has drained them
+        __syncwarp();
     }
 
     // ---------------------------------------------------------------------- teardown
