@@ -215,6 +215,10 @@ int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
 int jat_profile_begin(jat_ctx* ctx);
 int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts);
 
+/* Debug aid: when `buf` (DEVICE, 128 x int64) is non-NULL, CTA (0,0,0) of every following attention launch
+ * stores clock64() timestamps of its pipeline events there (scripts/att_trace.py decodes them). NULL = off. */
+int jat_debug_set_attention_trace(jat_ctx* ctx, void* buf);
+
 #ifdef __cplusplus
 }
 #endif

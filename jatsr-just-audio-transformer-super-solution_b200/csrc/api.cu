@@ -35,6 +35,7 @@ struct jat_ctx {
     std::vector<int> ev_tag;
     size_t ev_used;
     cudaStream_t cur_stream;
+    long long* att_trace;  // debug: device buffer of 128 clock64 slots for the attention kernel, or NULL
 };
 
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
@@ -93,6 +94,7 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->profiling = false;
     c->ev_used = 0;
     c->cur_stream = nullptr;
+    c->att_trace = nullptr;
     *out = c;
     return 0;
 }
@@ -109,6 +111,13 @@ extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
     if (block_n != 0 && block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "block_n must be 0/128/256");
     ctx->gemm_cta_pair = cta_pair ? 1 : 0;
     ctx->gemm_block_n = block_n;
+    return 0;
+}
+
+// Debug aid: timestamps (clock64) of the attention kernel's pipeline events, CTA (0,0,0); buf = 128 x int64 or NULL.
+extern "C" int jat_debug_set_attention_trace(jat_ctx* ctx, void* buf) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    ctx->att_trace = (long long*)buf;
     return 0;
 }
 
@@ -417,6 +426,7 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, i
     p.B = B; p.N = N; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
     p.out = (__nv_bfloat16*)out;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
+    p.trace = ctx->att_trace;
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));

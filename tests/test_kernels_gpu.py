@@ -262,3 +262,24 @@ def test_gqa_attention_rejects_long(ops, L):
     qkv = torch.zeros(400, 3 * 64, dtype=torch.bfloat16, device=dev())
     with pytest.raises(L.JatError):
         ops.gqa_attention_fwd(qkv, 1, 400, 1, 1)
+
+
+def test_gqa_attention_extreme_scores(ops):
+    """Keys with huge norm in one key half only: the two halves' row maxima differ by hundreds of nats, so
+    the split-KV combine weights 2^(m_half - m) underflow to exactly 0 on one side; results must stay
+    finite and equal the fp32 softmax (which is ~one-hot on that key)."""
+    torch.manual_seed(9)
+    B, N, Hq, Hkv, hd = 2, 345, 20, 4, 64
+    f = torch.randn(B, N, Hq + 2 * Hkv, hd, device=dev()) * 1.5
+    f[:, 300, Hq:Hq + Hkv] *= 25.0   # one key row with huge norm in every KV head
+    f[:, 171, Hq:Hq + Hkv] *= 60.0   # and a larger one in the other half
+    qkv = f.reshape(B * N, -1).to(torch.bfloat16)
+    got = ops.gqa_attention_fwd(qkv, B, N, Hq, Hkv)
+    assert torch.isfinite(got.float()).all()
+    g = qkv.float().view(B, N, Hq + 2 * Hkv, hd)
+    Q, K, V = g[:, :, :Hq], g[:, :, Hq:Hq + Hkv], g[:, :, Hq + Hkv:]
+    K = K.repeat_interleave(Hq // Hkv, dim=2)
+    V = V.repeat_interleave(Hq // Hkv, dim=2)
+    s = torch.matmul(Q.transpose(1, 2), K.transpose(1, 2).transpose(-2, -1)) / math.sqrt(hd)
+    want = torch.matmul(torch.softmax(s, -1), V.transpose(1, 2)).transpose(1, 2).reshape(B * N, Hq * hd)
+    assert rel_l2(got.float(), want) < 8e-3
