@@ -215,6 +215,29 @@ int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
 int jat_profile_begin(jat_ctx* ctx);
 int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts);
 
+/* ----------------------------------------------------------------------------------------------
+ * Long-audio chunk plumbing (infer_test_v3m2.py:340-406 chunk loop, :188-233 crossfade_chunks).
+ * A track latent[C, total_frames] (row pitch ld) is cut into chunks of `chunk_frames` frames starting every
+ * `stride` = chunk_frames - overlap frames.
+ *
+ * jat_chunk_normalize: out[k, c, t] = (latent[c, s_k + t] - mean[c]) / std[c] with
+ * s_k = (first_chunk + k * chunk_step) * stride, k < n_chunks; frames past the end of the track are 0
+ * (:377-382 for every chunk of a rank at once; chunk_step = world size gives the round-robin shard).
+ * mean == std == NULL copies without normalising.
+ *
+ * jat_crossfade_denorm: out[c, :] = left-fold linear crossfade (:188-233) of the chunks
+ * chunks[i, c, :] * std[c] + mean[c] (:394); fade_in / fade_out are the reference's
+ * torch.linspace(0, 1, overlap) / torch.linspace(1, 0, overlap) tables (f32 [overlap]).
+ * Requires chunk_frames >= 2 * overlap and (n-1)*stride + overlap < total_frames <= (n-1)*stride + chunk_frames.
+ * All arithmetic is unfused round-to-nearest fp32 in the reference's order: results are bit-identical.
+ * -------------------------------------------------------------------------------------------- */
+int jat_chunk_normalize(jat_ctx* ctx, const float* latent, int64_t total_frames, int64_t ld, const float* mean,
+                        const float* std, float* out, int n_chunks, int first_chunk, int chunk_step, int C,
+                        int chunk_frames, int stride, void* stream);
+int jat_crossfade_denorm(jat_ctx* ctx, const float* chunks, int n_chunks, int C, int chunk_frames, int overlap,
+                         const float* fade_in, const float* fade_out, const float* mean, const float* std, float* out,
+                         int64_t total_frames, int64_t ldo, void* stream);
+
 /* Debug aid: when `buf` (DEVICE, 128 x int64) is non-NULL, CTA (0,0,0) of every following attention launch
  * stores clock64() timestamps of its pipeline events there (scripts/att_trace.py decodes them). NULL = off. */
 int jat_debug_set_attention_trace(jat_ctx* ctx, void* buf);

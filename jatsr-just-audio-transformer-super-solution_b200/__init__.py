@@ -6,10 +6,12 @@ the top-level ``jat_b200.py`` shim, because hyphens are not importable).
 Public surface (mirrors the reference's):
     JaT_AudioSR_V2, JaT_AudioSR_V3     -- nn.Module drop-ins (src/models/jat_audiosr_v2.py / _v3.py)
     flow_matching_sample               -- Euler/CFG sampler drop-in (infer_test_v3m2.py:108)
+    chunked.sample_long / crossfade_chunks -- long-audio chunk loop + crossfade (infer_test_v3m2.py:340-406, 188-233)
 """
 from . import _lib  # noqa: F401
 from .models import JaT_AudioSR_V2, JaT_AudioSR_V3  # noqa: F401
 from .sampler import flow_matching_sample  # noqa: F401
+from . import chunked  # noqa: F401
 
-__all__ = ["JaT_AudioSR_V2", "JaT_AudioSR_V3", "flow_matching_sample", "_lib"]
+__all__ = ["JaT_AudioSR_V2", "JaT_AudioSR_V3", "flow_matching_sample", "chunked", "_lib"]
 __version__ = "0.1.0"

@@ -108,6 +108,8 @@ SIGNATURES = {
     "jat_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _vp]),
     "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_cfg_euler_update": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
+    "jat_chunk_normalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "jat_crossfade_denorm": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "jat_dit_modulation": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp]),
     "jat_dit_forward_tokens": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp, _i, _vp,
                                      _i64, _vp, _i, _i, _vp]),

@@ -12,6 +12,7 @@
 
 #include "../../include/jat_b200.h"
 #include "attention_gqa.cuh"
+#include "chunks.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
 
@@ -40,8 +41,9 @@ struct jat_ctx {
 
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
-                                          "cfg_euler_update", "gqa_attention_fwd"};
-enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_COUNT = 9 };
+                                          "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm"};
+enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_CHUNKN = 9,
+       TAG_XFADE = 10, TAG_COUNT = 11 };
 
 static thread_local char g_err[512] = "";
 
@@ -393,6 +395,45 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
     cfg_euler_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, x_c, x_u, cfg_scale, t_dt, step,
                                                                        (long long)numel);
     return post_launch(ctx, "cfg_euler_update");
+}
+
+// ------------------------------------------------------------------------------------------------ chunks
+extern "C" int jat_chunk_normalize(jat_ctx* ctx, const float* latent, int64_t total_frames, int64_t ld, const float* mean,
+                                   const float* std, float* out, int n_chunks, int first_chunk, int chunk_step, int C,
+                                   int chunk_frames, int stride, void* stream) {
+    if (!ctx || !latent || !out) return fail(JAT_ERR_BAD_ARG, "jat_chunk_normalize: null argument");
+    if ((mean == nullptr) != (std == nullptr)) return fail(JAT_ERR_BAD_ARG, "jat_chunk_normalize: mean and std go together");
+    if (n_chunks <= 0 || C <= 0 || chunk_frames <= 0 || stride <= 0 || first_chunk < 0 || chunk_step <= 0 ||
+        total_frames <= 0 || ld < total_frames || n_chunks > 65535 || C > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_chunk_normalize: bad sizes");
+    dim3 grid((chunk_frames + 255) / 256, C, n_chunks);
+    pre_launch(ctx, TAG_CHUNKN, (cudaStream_t)stream);
+    chunk_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latent, (long long)total_frames, (long long)ld, mean, std,
+                                                                   out, C, chunk_frames, stride, first_chunk, chunk_step);
+    return post_launch(ctx, "chunk_normalize");
+}
+
+extern "C" int jat_crossfade_denorm(jat_ctx* ctx, const float* chunks, int n_chunks, int C, int chunk_frames, int overlap,
+                                    const float* fade_in, const float* fade_out, const float* mean, const float* std,
+                                    float* out, int64_t total_frames, int64_t ldo, void* stream) {
+    if (!ctx || !chunks || !out) return fail(JAT_ERR_BAD_ARG, "jat_crossfade_denorm: null argument");
+    if ((mean == nullptr) != (std == nullptr)) return fail(JAT_ERR_BAD_ARG, "jat_crossfade_denorm: mean and std go together");
+    if (n_chunks <= 0 || C <= 0 || C > 65535 || chunk_frames <= 0 || overlap < 0 || total_frames <= 0 || ldo < total_frames)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_crossfade_denorm: bad sizes");
+    if (overlap > 0 && (!fade_in || !fade_out)) return fail(JAT_ERR_BAD_ARG, "jat_crossfade_denorm: fade tables missing");
+    if (n_chunks > 1 && chunk_frames < 2 * overlap)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_crossfade_denorm: chunk_frames (%d) < 2 * overlap (%d)", chunk_frames, overlap);
+    const int64_t stride = chunk_frames - overlap;
+    if (total_frames > (int64_t)(n_chunks - 1) * stride + chunk_frames || total_frames <= (int64_t)(n_chunks - 1) * stride + overlap)
+        if (!(n_chunks == 1 && total_frames <= chunk_frames))
+            return fail(JAT_ERR_BAD_SHAPE, "jat_crossfade_denorm: total_frames %lld does not match %d chunks",
+                        (long long)total_frames, n_chunks);
+    dim3 grid((unsigned)((total_frames + 255) / 256), C);
+    pre_launch(ctx, TAG_XFADE, (cudaStream_t)stream);
+    crossfade_denorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, n_chunks, C, chunk_frames, overlap, fade_in,
+                                                                    fade_out, mean, std, out, (long long)total_frames,
+                                                                    (long long)ldo);
+    return post_launch(ctx, "crossfade_denorm");
 }
 
 // ------------------------------------------------------------------------------------------------ attention

@@ -120,3 +120,31 @@ def cfg_euler_update(z, x_c, x_u, cfg_scale, t_dt, step):
     L.check(L.load().jat_cfg_euler_update(_ctx(z), z.data_ptr(), x_c.data_ptr(), _p(x_u), float(cfg_scale),
                                           t_dt.data_ptr(), step, z.numel(), _stream(z.device)))
     return z
+
+
+def chunk_normalize(latent, n_chunks, chunk_frames, stride, mean=None, std=None, first_chunk=0, chunk_step=1, out=None):
+    """latent f32 [C, total] (row pitch = stride(0)) -> f32 [n_chunks, C, chunk_frames] normalised chunk batch."""
+    if latent.dtype != torch.float32 or latent.dim() != 2 or latent.stride(1) != 1:
+        raise ValueError("latent: expected f32 [C, total] with unit inner stride")
+    Cc, total = latent.shape
+    if out is None:
+        out = torch.empty(n_chunks, Cc, chunk_frames, dtype=torch.float32, device=latent.device)
+    for v, n in ((mean, "mean"), (std, "std")):
+        if v is not None:
+            _chk(v, torch.float32, n)
+    L.check(L.load().jat_chunk_normalize(_ctx(latent), latent.data_ptr(), total, latent.stride(0), _p(mean), _p(std),
+                                         out.data_ptr(), n_chunks, first_chunk, chunk_step, Cc, chunk_frames, stride,
+                                         _stream(latent.device)))
+    return out
+
+
+def crossfade_denorm(chunks, overlap, total_frames, fade_in=None, fade_out=None, mean=None, std=None, out=None):
+    """chunks f32 [n, C, Tc] -> f32 [C, total_frames]: (chunk * std + mean) stitched with the linear crossfade."""
+    _chk(chunks, torch.float32, "chunks")
+    n, Cc, Tc = chunks.shape
+    if out is None:
+        out = torch.empty(Cc, total_frames, dtype=torch.float32, device=chunks.device)
+    L.check(L.load().jat_crossfade_denorm(_ctx(chunks), chunks.data_ptr(), n, Cc, Tc, overlap, _p(fade_in), _p(fade_out),
+                                          _p(mean), _p(std), out.data_ptr(), total_frames, out.stride(0),
+                                          _stream(chunks.device)))
+    return out

@@ -227,3 +227,58 @@ def flow_matching_sample(p, lr_latent, z0, *, num_steps=50, cfg_scale=1.0, num_q
             x_c, x_u = dit_forward(p, z, tb, lr, **kw).astype(np.float32), None
         z = euler_cfg_update(z, x_c, x_u, cfg_scale, t, dt)
     return z
+
+
+# ------------------------------------------------------------------------------------------- long-audio chunk loop
+def plan_chunks(total_frames, chunk_frames=1378, overlap_frames=172):
+    """Chunk boundaries of infer_test_v3m2.py:358-372: stride = chunk - overlap,
+    num_chunks = ceil((total - overlap) / stride), chunk i = [i*stride, min(i*stride + chunk, total))."""
+    stride = chunk_frames - overlap_frames
+    n = (total_frames - overlap_frames + stride - 1) // stride
+    return [(i * stride, min(i * stride + chunk_frames, total_frames)) for i in range(n)]
+
+
+def linspace_f32(start, end, steps):
+    """torch.linspace(start, end, steps) in fp32: ATen fills symmetrically from both ends with a fused multiply-add
+    (RangeFactories; same on CPU-vectorised and CUDA) -- emulated in float64 with the fp32 step (cf. sampler_schedule)."""
+    if steps == 1:
+        return np.array([start], dtype=np.float32)
+    step = np.float64(np.float32((np.float32(end) - np.float32(start)) / np.float32(steps - 1)))
+    i = np.arange(steps)
+    lo = (np.float64(np.float32(start)) + step * i).astype(np.float32)
+    hi = (np.float64(np.float32(end)) - step * (steps - 1 - i)).astype(np.float32)
+    return np.where(i < steps // 2, lo, hi).astype(np.float32)
+
+
+def crossfade_chunks(chunks, overlap_frames):
+    """crossfade_chunks (infer_test_v3m2.py:188-233): left fold over [1, C, T_i] chunks; in every overlap the running
+    result fades out with linspace(1, 0, overlap) and the new chunk fades in with linspace(0, 1, overlap)."""
+    if len(chunks) == 0:
+        return None
+    result = np.asarray(chunks[0], dtype=np.float32)
+    for cur in chunks[1:]:
+        cur = np.asarray(cur, dtype=np.float32)
+        if overlap_frames > 0 and result.shape[-1] >= overlap_frames:
+            fo = linspace_f32(1.0, 0.0, overlap_frames).reshape(1, 1, -1)
+            fi = linspace_f32(0.0, 1.0, overlap_frames).reshape(1, 1, -1)
+            blended = ((result[..., -overlap_frames:] * fo).astype(np.float32)
+                       + (cur[..., :overlap_frames] * fi).astype(np.float32)).astype(np.float32)
+            result = np.concatenate([result[..., :-overlap_frames], blended, cur[..., overlap_frames:]], axis=-1)
+        else:
+            result = np.concatenate([result, cur], axis=-1)
+    return result
+
+
+def sample_long(sample_fn, lr_latent, lr_mean, lr_std, hr_mean, hr_std, chunk_frames=1378, overlap_frames=172,
+                total_frames=None):
+    """The chunk loop of infer_test_v3m2.py:370-402 around an arbitrary per-chunk sampler `sample_fn(lr_norm[1,C,T],
+    chunk_index) -> [1,C,T]`: normalise (:381-382), sample (:385), de-normalise (:394), crossfade (:402)."""
+    lr_latent = np.asarray(lr_latent, dtype=np.float32)
+    total = lr_latent.shape[-1] if total_frames is None else min(total_frames, lr_latent.shape[-1])
+    outs = []
+    for i, (s, e) in enumerate(plan_chunks(total, chunk_frames, overlap_frames)):
+        lr = lr_latent[None, :, s:e]
+        lr_norm = ((lr - lr_mean) / lr_std).astype(np.float32)
+        gen = np.asarray(sample_fn(lr_norm, i), dtype=np.float32)
+        outs.append(((gen * hr_std).astype(np.float32) + hr_mean).astype(np.float32))
+    return crossfade_chunks(outs, overlap_frames)
