@@ -82,12 +82,15 @@ int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf16, int B, i
 /* ----------------------------------------------------------------------------------------------
  * tcgen05 / TMEM GEMM fed by TMA:  acc[M, N] = A[M, K] (bf16, row pitch lda) * W[N, K]^T (bf16,
  * nn.Linear layout, row pitch ldw), fp32 accumulation in tensor memory, fused epilogue.
- * Requirements: K % 64 == 0, N % 128 == 0, lda/ldw % 8 == 0, 16-byte aligned pointers.
+ * Requirements: N % 128 == 0, lda/ldw % 8 == 0, 16-byte aligned pointers; K % 64 == 0 unless both operands are
+ * given transposed (then the TMA unit zero-fills the reduction rows past K).
  * -------------------------------------------------------------------------------------------- */
 #define JAT_EPI_BIAS_ACT 0      /* out = act(acc + bias)                  (Linear [+GELU|SiLU])      */
 #define JAT_EPI_QKV_ROPE 1      /* out = RoPE(acc) on columns < rope_cols (q_proj/k_proj/v_proj+RoPE) */
 #define JAT_EPI_GATE_RESIDUAL 2 /* out(f32, in place) += gate[b,:] * (acc + bias)   (adaLN-Zero gate) */
 #define JAT_EPI_UNPATCHIFY 3    /* out[b, c, n*P+p] = acc[m, c*P+p] + bias  (final Linear+unpatchify) */
+#define JAT_EPI_ACCUM 4         /* out(f32, in place) += acc (+ bias)      (weight gradients, split-K partial sums) */
+#define JAT_EPI_DACT 5          /* out(bf16) = (acc + bias) * act'(aux)    (dgrad through GELU / SiLU; aux = pre-activation) */
 
 #define JAT_ACT_NONE 0
 #define JAT_ACT_GELU_ERF 1 /* nn.GELU() default (exact erf form), jat_audiosr_v2.py:206,249 */
@@ -111,7 +114,14 @@ typedef struct jat_gemm_epilogue {
     int32_t rope_cols; /* QKV_ROPE: columns [0, rope_cols) are 64-wide heads to rotate (Q and K) */
     int32_t patch_len; /* UNPATCHIFY: P (must be 4) */
     int32_t t_out;     /* UNPATCHIFY: cropped length T (<= tokens_per_batch * P) */
-    int32_t reserved;
+    int32_t k_splits;  /* GATE_RESIDUAL / ACCUM: split the reduction over this many work items per tile (0 or 1 = off) */
+    void* aux;         /* DACT: pre-activation u bf16 [M, ld_aux] (read).  BIAS_ACT/bf16: if non-NULL, a bf16 copy of
+                          acc + bias (the pre-activation) is written here for the backward pass */
+    int64_t ld_aux;
+    int32_t a_transposed; /* 1: A is given as A^T [K, M] row-major with pitch lda (reduction index = row) */
+    int32_t w_transposed; /* 1: W is given as W^T [K, N] row-major with pitch ldw.  Backward GEMMs without copies:
+                             dgrad dX = dY W      -> A = dY, W = weight with w_transposed = 1;
+                             wgrad dW = dY^T X    -> A = dY with a_transposed = 1, W = X with w_transposed = 1 */
 } jat_gemm_epilogue;
 
 /* cta_pair: 0 = one CTA per 128-row tile (tcgen05 cta_group::1), 1 = CTA pair per 256-row tile

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 # ---- enums mirrored from include/jat_b200.h
 NORM_LAYERNORM, NORM_RMSNORM = 0, 1
-EPI_BIAS_ACT, EPI_QKV_ROPE, EPI_GATE_RESIDUAL, EPI_UNPATCHIFY = 0, 1, 2, 3
+EPI_BIAS_ACT, EPI_QKV_ROPE, EPI_GATE_RESIDUAL, EPI_UNPATCHIFY, EPI_ACCUM, EPI_DACT = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_GELU_ERF, ACT_SILU = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ERR_SEQ_TOO_LONG = -5
@@ -58,7 +58,8 @@ class GemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64),
         ("gate", C.c_void_p), ("gate_batch_stride", C.c_int64),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
-        ("rope_cols", C.c_int32), ("patch_len", C.c_int32), ("t_out", C.c_int32), ("reserved", C.c_int32),
+        ("rope_cols", C.c_int32), ("patch_len", C.c_int32), ("t_out", C.c_int32), ("k_splits", C.c_int32),
+        ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("a_transposed", C.c_int32), ("w_transposed", C.c_int32),
     ]
 
 

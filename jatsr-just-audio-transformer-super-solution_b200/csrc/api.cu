@@ -41,9 +41,10 @@ struct jat_ctx {
 
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
-                                          "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm"};
+                                          "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm",
+                                          "gemm_accum", "gemm_dact"};
 enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_CHUNKN = 9,
-       TAG_XFADE = 10, TAG_COUNT = 11 };
+       TAG_XFADE = 10, TAG_GEMM_ACCUM = 11, TAG_GEMM_DACT = 12, TAG_COUNT = 13 };
 
 static thread_local char g_err[512] = "";
 
@@ -195,18 +196,18 @@ static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t ro
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0>
 static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                        const GemmParams& p, cudaStream_t s) {
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16>;
+    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     int clusters = ctx->sm_count / CG;
-    if (clusters > p.num_tiles) clusters = p.num_tiles;
+    if (clusters > p.num_tiles * p.k_splits) clusters = p.num_tiles * p.k_splits;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -219,7 +220,7 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    pre_launch(ctx, TAG_GEMM0 + EPI, s);
+    pre_launch(ctx, EPI <= EPI_UNPATCHIFY ? TAG_GEMM0 + EPI : (EPI == EPI_ACCUM ? TAG_GEMM_ACCUM : TAG_GEMM_DACT), s);
     JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
     return post_launch(ctx, "gemm_tcgen05");
 }
@@ -227,6 +228,30 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
 template <int BN, int CG>
 static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                              const GemmParams& p, const jat_gemm_epilogue* e, cudaStream_t s) {
+    const int amn = e->a_transposed ? 1 : 0, bmn = e->w_transposed ? 1 : 0;
+    if (amn && bmn) {  // wgrad
+        if (e->kind == JAT_EPI_ACCUM) return launch_gemm<BN, CG, EPI_ACCUM, ACT_NONE, 0, 1, 1>(ctx, ta, tb, to, p, s);
+        return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: both operands transposed is supported with JAT_EPI_ACCUM only");
+    }
+    if (bmn) {  // dgrad
+        switch (e->kind) {
+            case JAT_EPI_BIAS_ACT:
+                if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_BF16)
+                    return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 1, 0, 1>(ctx, ta, tb, to, p, s);
+                if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_F32)
+                    return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 0, 0, 1>(ctx, ta, tb, to, p, s);
+                break;
+            case JAT_EPI_ACCUM:
+                return launch_gemm<BN, CG, EPI_ACCUM, ACT_NONE, 0, 0, 1>(ctx, ta, tb, to, p, s);
+            case JAT_EPI_DACT:
+                if (e->act == JAT_ACT_GELU_ERF) return launch_gemm<BN, CG, EPI_DACT, ACT_GELU, 1, 0, 1>(ctx, ta, tb, to, p, s);
+                if (e->act == JAT_ACT_SILU) return launch_gemm<BN, CG, EPI_DACT, ACT_SILU, 1, 0, 1>(ctx, ta, tb, to, p, s);
+                break;
+        }
+        return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unsupported epilogue (%d, act %d, dtype %d) with w_transposed", e->kind,
+                    e->act, e->out_dtype);
+    }
+    if (amn) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: a_transposed needs w_transposed");
     switch (e->kind) {
         case JAT_EPI_BIAS_ACT:
             if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_F32)
@@ -246,14 +271,15 @@ static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
         case JAT_EPI_UNPATCHIFY:
             return launch_gemm<BN, CG, EPI_UNPATCHIFY, ACT_NONE, 0>(ctx, ta, tb, to, p, s);
     }
-    return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
+    return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unsupported epilogue kind %d for untransposed operands", e->kind);
 }
 
 extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                              const jat_gemm_epilogue* e, int cta_pair, int block_n, void* stream) {
     if (!ctx || !A || !W || !e || !e->out) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: null argument");
     if (M <= 0 || N <= 0 || K <= 0) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: non-positive size");
-    if (K % 64 != 0 || N % 128 != 0)
+    const bool a_mn = e->a_transposed != 0, w_mn = e->w_transposed != 0;
+    if ((K % 64 != 0 && !(a_mn && w_mn)) || N % 128 != 0)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
     if (cta_pair < 0) cta_pair = ctx->gemm_cta_pair;
     if (block_n == 0) block_n = ctx->gemm_block_n;
@@ -265,7 +291,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.num_n_blocks = N / block_n;
-    p.num_k_blocks = K / GEMM_BK;
+    p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
     const int rows_per_tile = GEMM_BM * cg;
     p.num_tiles = ((M + rows_per_tile - 1) / rows_per_tile) * p.num_n_blocks;
     p.bias = e->bias;
@@ -278,6 +304,12 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     p.rope_sin = e->rope_sin;
     p.rope_cols = e->rope_cols;
     p.t_out = e->t_out;
+    p.aux = e->aux;
+    p.ld_aux = e->ld_aux;
+    p.k_splits = e->k_splits > 1 ? e->k_splits : 1;
+    if (p.k_splits > 1 && e->kind != JAT_EPI_GATE_RESIDUAL && e->kind != JAT_EPI_ACCUM)
+        return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: k_splits needs a reduce-add epilogue (GATE_RESIDUAL / ACCUM)");
+    if (p.k_splits > p.num_k_blocks) p.k_splits = p.num_k_blocks;
 
     switch (e->kind) {
         case JAT_EPI_BIAS_ACT:
@@ -291,6 +323,13 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
             if (!e->gate || e->ldo % 4 != 0 || e->gate_batch_stride % 4 != 0)
                 return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: GATE_RESIDUAL needs gate and 16B-aligned pitches");
             break;
+        case JAT_EPI_ACCUM:
+            if (e->ldo % 4 != 0) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: ACCUM needs a 16B-aligned output pitch");
+            break;
+        case JAT_EPI_DACT:
+            if (!e->aux || e->ld_aux % 8 != 0 || e->ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(e->aux) & 15) != 0)
+                return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: DACT needs a 16B-aligned aux (pre-activation) operand");
+            break;
         case JAT_EPI_UNPATCHIFY:
             if (e->patch_len != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: UNPATCHIFY supports patch_len 4 only");
             if (e->t_out <= 0 || e->t_out > p.tokens_per_batch * 4)
@@ -300,14 +339,21 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
             return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: unknown epilogue kind %d", e->kind);
     }
 
+    if (e->kind == JAT_EPI_BIAS_ACT && e->aux != nullptr &&
+        (e->out_dtype != JAT_DTYPE_BF16 || e->ld_aux % 8 != 0 || (reinterpret_cast<uintptr_t>(e->aux) & 15) != 0))
+        return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: the pre-activation copy (aux) needs bf16 output and 16B alignment");
     CUtensorMap ta, tb, to;
-    JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
-    JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg)));
+    // transposed operands: rows = reduction index, boxes of 64 reduction rows x 64 M/N elements
+    if (a_mn) JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64));
+    else JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
+    if (w_mn) JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 64));
+    else JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg)));
     if (e->kind == JAT_EPI_UNPATCHIFY) {
         to = ta;  // unused by that epilogue
     } else {
         // epilogue slabs: 32 rows x 128 bytes, stored (or reduce-added) by the TMA unit; rows >= M are clipped
-        const bool out_f32 = e->kind == JAT_EPI_GATE_RESIDUAL || (e->kind == JAT_EPI_BIAS_ACT && e->out_dtype == JAT_DTYPE_F32);
+        const bool out_f32 = e->kind == JAT_EPI_GATE_RESIDUAL || e->kind == JAT_EPI_ACCUM ||
+                             (e->kind == JAT_EPI_BIAS_ACT && e->out_dtype == JAT_DTYPE_F32);
         JAT_TRY(make_tmap(ctx, &to, e->out, (uint64_t)M, (uint64_t)N, (uint64_t)e->ldo, 32, out_f32));
     }
     cudaStream_t s = (cudaStream_t)stream;

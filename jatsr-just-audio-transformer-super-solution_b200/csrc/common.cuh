@@ -99,6 +99,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* tmap, uin
         : "memory");
 }
 
+template <int kCtaGroup>
+__device__ __forceinline__ void tma_load_tile(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+    if constexpr (kCtaGroup == 1) tma_load_2d(dst, tmap, bar, c0, c1);
+    else tma_load_2d_2sm(dst, tmap, bar, c0, c1);
+}
+
 // 2D tile store smem -> global (bulk async-group completion). Out-of-bounds rows/cols are clipped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -283,6 +289,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// MN-major operand: the tile is a row of TMA boxes, each [64 reduction rows x 64 M/N elements (128 B)], 128B swizzle,
+// `box_bytes` apart.  leading byte offset = distance between boxes (next 64 M/N elements), stride byte offset =
+// 1024 (next 8 reduction rows); a 16-row k-step advances the start address by 16 x 128 B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t box_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((box_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;

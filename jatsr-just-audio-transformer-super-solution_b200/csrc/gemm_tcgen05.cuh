@@ -26,7 +26,7 @@
 
 namespace jat {
 
-enum { EPI_BIAS_ACT = 0, EPI_QKV_ROPE = 1, EPI_GATE_RESIDUAL = 2, EPI_UNPATCHIFY = 3 };
+enum { EPI_BIAS_ACT = 0, EPI_QKV_ROPE = 1, EPI_GATE_RESIDUAL = 2, EPI_UNPATCHIFY = 3, EPI_ACCUM = 4, EPI_DACT = 5 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
 struct GemmParams {
@@ -42,6 +42,9 @@ struct GemmParams {
     const float* rope_sin;
     int rope_cols;
     int t_out;
+    int k_splits;            // split-K: every output tile is computed by k_splits work items (reduce-add epilogues only)
+    const void* aux;         // EPI_DACT: pre-activation u bf16 [M, ld_aux];  EPI_BIAS_ACT: optional bf16 copy of (acc + bias)
+    long long ld_aux;
 };
 
 constexpr int GEMM_BM = 128;
@@ -71,6 +74,20 @@ __device__ __forceinline__ float apply_act(float v) {
     return v;
 }
 
+// derivative of the activation at pre-activation u (backward of mlp.1 / patch_embed.proj.1 GELU, t_embedder.2 SiLU)
+template <int ACT>
+__device__ __forceinline__ float dact(float u) {
+    if constexpr (ACT == ACT_GELU) {  // d/du [u Phi(u)] = Phi(u) + u phi(u)
+        const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+        return fmaf(u * 0.3989422804014327f, __expf(-0.5f * u * u), cdf);
+    }
+    if constexpr (ACT == ACT_SILU) {  // d/du [u sigma(u)] = sigma(u) (1 + u (1 - sigma(u)))
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        return sg * fmaf(u, 1.0f - sg, 1.0f);
+    }
+    return 1.0f;
+}
+
 // 16-byte chunk `chunk` (0..7) of row `lane` inside a 128B-swizzled 32-row slab
 __device__ __forceinline__ void st_slab_chunk(uint32_t slab_row_addr, int lane, int chunk, uint32_t a, uint32_t b,
                                               uint32_t c, uint32_t d) {
@@ -78,7 +95,13 @@ __device__ __forceinline__ void st_slab_chunk(uint32_t slab_row_addr, int lane, 
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16>
+// A_MN / B_MN: the operand is stored "MN-major" = as the TRANSPOSE of the K-major layout, i.e. A^T [K, M] /
+// W^T [K, N] row-major (reduction index = row).  That is what the backward GEMMs see without any transposed
+// copies:  dgrad  dX[M, K'] = dY[M, N'] W[N', K']      -> B_MN (W rows = reduction index)
+//          wgrad  dW[N', K'] = dY^T[N', M] X[M, K']    -> A_MN and B_MN (token index = reduction index)
+// Tiles are then TMA boxes of 64 reduction rows x 64 elements (128 B), one box per 64 output rows/columns,
+// consumed through MN-major UMMA descriptors (leading byte offset = one 8 KB box).
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -133,23 +156,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            const int num_work = p.num_tiles * p.k_splits;
+            for (int work = cluster_id; work < num_work; work += num_clusters) {
+                const int tile = work / p.k_splits, part = work - tile * p.k_splits;
+                const int kb0 = (int)((long long)p.num_k_blocks * part / p.k_splits);
+                const int kb1 = (int)((long long)p.num_k_blocks * (part + 1) / p.k_splits);
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
                 const int a_row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM;
                 const int b_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    if constexpr (CG == 1) {
-                        mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
-                        tma_load_2d(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
+                    if (CG == 1) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
+                    else if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES * 2);  // both CTAs' bytes
+                    if constexpr (A_MN) {  // boxes of 64 reduction rows x 64 output rows (8 KB each)
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j)
+                            tma_load_tile<CG>(sa + j * 8192, &tmap_a, &bar_full[stage], a_row0 + j * 64, kb * GEMM_BK);
                     } else {
-                        // both CTAs' bytes complete on the leader's barrier
-                        if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES * 2);
-                        tma_load_2d_2sm(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
-                        tma_load_2d_2sm(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
+                        tma_load_tile<CG>(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < Cfg::B_ROWS / 64; ++j)
+                            tma_load_tile<CG>(sb + j * 8192, &tmap_b, &bar_full[stage], b_row0 + j * 64, kb * GEMM_BK);
+                    } else {
+                        tma_load_tile<CG>(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -159,27 +192,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (cta_rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, A_MN, B_MN);
+            // per 16-element k-step: +32 B inside the 128B swizzle atom (K-major) or +16 rows x 128 B (MN-major)
+            constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : 2u, b_kstep = B_MN ? (2048u >> 4) : 2u;
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            const int num_work = p.num_tiles * p.k_splits;
+            for (int work = cluster_id; work < num_work; work += num_clusters) {
+                const int tile = work / p.k_splits, part = work - tile * p.k_splits;
+                const int kb0 = (int)((long long)p.num_k_blocks * part / p.k_splits);
+                const int kb1 = (int)((long long)p.num_k_blocks * (part + 1) / p.k_splits);
                 mbar_wait(&bar_tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint64_t a_desc = umma_smem_desc_sw128(sa);
-                        const uint64_t b_desc = umma_smem_desc_sw128(sa + Cfg::A_BYTES);
+                        const uint64_t a_desc = A_MN ? umma_smem_desc_sw128_mn(sa, 8192) : umma_smem_desc_sw128(sa);
+                        const uint64_t b_desc = B_MN ? umma_smem_desc_sw128_mn(sa + Cfg::A_BYTES, 8192)
+                                                     : umma_smem_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) {
-                            // +32 bytes (16 bf16) along K inside the 128B swizzle atom = +2 in the address field
-                            umma_bf16_ss<CG>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                        }
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                            umma_bf16_ss<CG>(d_tmem, a_desc + a_kstep * k, b_desc + b_kstep * k, idesc,
+                                             (uint32_t)((kb != kb0) | (k != 0)));
                         if constexpr (CG == 1) umma_commit(&bar_empty[stage]);
                         else umma_commit_2sm(&bar_empty[stage], 0x3);
                     }
@@ -206,7 +245,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        const int num_work = p.num_tiles * p.k_splits;
+        for (int work = cluster_id; work < num_work; work += num_clusters) {
+            const int tile = work / p.k_splits, part = work - tile * p.k_splits;
+            const bool add_bias = p.bias != nullptr && part == 0;  // split-K: the bias goes in with the first partial sum
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
             const int row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM + quad * 32;  // first row of this warp's slab
             const int m = row0 + lane;
@@ -216,7 +258,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + wg * HALF);
 
-            if constexpr (EPI == EPI_BIAS_ACT && OUT_BF16) {
+            if constexpr ((EPI == EPI_BIAS_ACT && OUT_BF16) || EPI == EPI_DACT) {
+                // BIAS_ACT: out = act(acc + bias)  [+ optional bf16 copy of the pre-activation acc + bias to p.aux,
+                //           kept by the training forward for the backward of the activation]
+                // DACT:     out = (acc + bias) * act'(u),  u = pre-activation read from p.aux   (dgrad through GELU)
+                const __nv_bfloat16* aux_row =
+                    reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)(row_ok ? m : 0) * p.ld_aux;
+                const bool use_aux = p.aux != nullptr && row_ok;
 #pragma unroll 1
                 for (int sl = 0; sl < HALF / 64; ++sl) {  // slab = 64 bf16 columns
                     const int n0 = n_base + sl * 64;
@@ -232,12 +280,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             float f[8];
 #pragma unroll
                             for (int q = 0; q < 8; q += 4) {
-                                const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hx * 32 + j + q))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                                f[q + 0] = apply_act<ACT>(__uint_as_float(v[j + q + 0]) + b4.x);
-                                f[q + 1] = apply_act<ACT>(__uint_as_float(v[j + q + 1]) + b4.y);
-                                f[q + 2] = apply_act<ACT>(__uint_as_float(v[j + q + 2]) + b4.z);
-                                f[q + 3] = apply_act<ACT>(__uint_as_float(v[j + q + 3]) + b4.w);
+                                const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hx * 32 + j + q))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                                f[q + 0] = __uint_as_float(v[j + q + 0]) + b4.x;
+                                f[q + 1] = __uint_as_float(v[j + q + 1]) + b4.y;
+                                f[q + 2] = __uint_as_float(v[j + q + 2]) + b4.z;
+                                f[q + 3] = __uint_as_float(v[j + q + 3]) + b4.w;
+                            }
+                            if constexpr (EPI == EPI_DACT) {
+                                uint4 u4 = make_uint4(0u, 0u, 0u, 0u);
+                                if (use_aux) u4 = __ldg(reinterpret_cast<const uint4*>(aux_row + n0 + hx * 32 + j));
+                                const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    f[2 * q] *= dact<ACT>(__uint_as_float(uw[q] << 16));
+                                    f[2 * q + 1] *= dact<ACT>(__uint_as_float(uw[q] & 0xffff0000u));
+                                }
+                            } else {
+                                if (use_aux)
+                                    *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(aux_row) + n0 + hx * 32 + j) =
+                                        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                   pack_bf16(f[6], f[7]));
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) f[q] = apply_act<ACT>(f[q]);
                             }
                             st_slab_chunk(slab_row[buf], lane, hx * 4 + j / 8, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
                                           pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -251,8 +316,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     buf ^= 1;
                 }
-            } else if constexpr (EPI == EPI_BIAS_ACT || EPI == EPI_GATE_RESIDUAL) {
+            } else if constexpr (EPI == EPI_BIAS_ACT || EPI == EPI_GATE_RESIDUAL || EPI == EPI_ACCUM) {
                 // f32 slabs of 32 columns.  GATE_RESIDUAL: slab = gate * (acc + bias), TMA-reduce-added into x.
+                // ACCUM: slab = acc (+ bias), TMA-reduce-added into out (gradient accumulation, split-K partial sums).
                 const float* grow = nullptr;
                 if constexpr (EPI == EPI_GATE_RESIDUAL)
                     grow = p.gate + (long long)(row_ok ? (m / p.tokens_per_batch) : 0) * p.gate_bstride;
@@ -266,14 +332,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                        const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                         float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
                               r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
                         if constexpr (EPI == EPI_GATE_RESIDUAL) {
                             const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
                             r0 *= g4.x; r1 *= g4.y; r2 *= g4.z; r3 *= g4.w;
-                        } else {
+                        } else if constexpr (EPI == EPI_BIAS_ACT) {
                             r0 = apply_act<ACT>(r0); r1 = apply_act<ACT>(r1); r2 = apply_act<ACT>(r2); r3 = apply_act<ACT>(r3);
                         }
                         st_slab_chunk(slab_row[buf], lane, j / 4, __float_as_uint(r0), __float_as_uint(r1),
@@ -283,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     __syncwarp();
                     if (lane == 0) {
                         if (row0 < p.M) {
-                            if constexpr (EPI == EPI_GATE_RESIDUAL)
+                            if constexpr (EPI == EPI_GATE_RESIDUAL || EPI == EPI_ACCUM)
                                 tma_reduce_add_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
                             else
                                 tma_store_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);

@@ -73,17 +73,18 @@ def timestep_features(t, D, out=None):
 
 def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, bias=None, out=None,
          gate=None, gate_batch_stride=0, tokens_per_batch=0, rope_cos=None, rope_sin=None, rope_cols=0,
-         patch_len=4, t_out=0, cta_pair=-1, block_n=0):
-    """acc = A[M,K] @ W[N,K]^T (bf16 in, f32 accumulate) + fused epilogue; returns `out`."""
+         patch_len=4, t_out=0, cta_pair=-1, block_n=0, aux=None, k_splits=0, a_transposed=False, w_transposed=False):
+    """acc = A[M,K] @ W[N,K]^T (bf16 in, f32 accumulate) + fused epilogue; returns `out`.
+    a_transposed / w_transposed: the tensor passed holds A^T [K, M] / W^T [K, N] (backward GEMMs, no copies)."""
     _chk(A, torch.bfloat16, "A")
     _chk(W, torch.bfloat16, "W")
-    M, K = A.shape
-    N, K2 = W.shape
-    assert K == K2
+    (K, M) = A.shape if a_transposed else A.shape[::-1]
+    (K2, N) = W.shape if w_transposed else W.shape[::-1]
+    assert K == K2, (A.shape, W.shape)
     if out is None:
-        if kind == L.EPI_BIAS_ACT:
-            out = torch.empty(M, N, dtype=torch.bfloat16 if out_dtype == L.DTYPE_BF16 else torch.float32,
-                              device=A.device)
+        if kind in (L.EPI_BIAS_ACT, L.EPI_DACT):
+            bf = out_dtype == L.DTYPE_BF16 or kind == L.EPI_DACT
+            out = torch.empty(M, N, dtype=torch.bfloat16 if bf else torch.float32, device=A.device)
         elif kind == L.EPI_QKV_ROPE:
             out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
         else:
@@ -94,7 +95,9 @@ def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, b
     e.ldo = out.stride(0) if kind != L.EPI_UNPATCHIFY else 0
     e.gate, e.gate_batch_stride = _p(gate), gate_batch_stride
     e.rope_cos, e.rope_sin, e.rope_cols = _p(rope_cos), _p(rope_sin), rope_cols
-    e.patch_len, e.t_out = patch_len, t_out
+    e.patch_len, e.t_out, e.k_splits = patch_len, t_out, k_splits
+    e.aux, e.ld_aux = _p(aux), (aux.stride(0) if aux is not None else 0)
+    e.a_transposed, e.w_transposed = int(a_transposed), int(w_transposed)
     L.check(L.load().jat_gemm_bf16(_ctx(A), A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K,
                                    C.byref(e), cta_pair, block_n, _stream(A.device)))
     return out

@@ -283,3 +283,83 @@ def test_gqa_attention_extreme_scores(ops):
     s = torch.matmul(Q.transpose(1, 2), K.transpose(1, 2).transpose(-2, -1)) / math.sqrt(hd)
     want = torch.matmul(torch.softmax(s, -1), V.transpose(1, 2)).transpose(1, 2).reshape(B * N, Hq * hd)
     assert rel_l2(got.float(), want) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ backward GEMMs
+def _gelu_grad(u):
+    return 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("M,Nfwd,Kfwd", [(300, 512, 1280), (1000, 1280, 256), (56, 128, 128)])
+def test_gemm_dgrad_transposed_weight(ops, L, cta_pair, block_n, M, Nfwd, Kfwd):
+    """dX[M, K'] = dY[M, N'] W[N', K'] with W passed as stored (nn.Linear [out, in]) via w_transposed."""
+    torch.manual_seed(3)
+    dY = torch.randn(M, Nfwd, device=dev()).to(torch.bfloat16)
+    W = (torch.randn(Nfwd, Kfwd, device=dev()) / math.sqrt(Nfwd)).to(torch.bfloat16)
+    got = ops.gemm(dY, W, w_transposed=True, cta_pair=cta_pair, block_n=block_n)
+    want = dY.float() @ W.float()
+    assert got.shape == (M, Kfwd) and rel_l2(got.float(), want) < 4e-3
+    got32 = ops.gemm(dY, W, w_transposed=True, out_dtype=L.DTYPE_F32, cta_pair=cta_pair, block_n=block_n)
+    assert rel_l2(got32, want) < 1e-5
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_dgrad_through_activation(ops, L, cta_pair, block_n, act):
+    """du = (dY W) * act'(u): dgrad of mlp.3 fused with the GELU backward (and SiLU for t_embedder)."""
+    torch.manual_seed(4)
+    M, Nfwd, Kfwd = 333, 256, 1280
+    dY = torch.randn(M, Nfwd, device=dev()).to(torch.bfloat16)
+    W = (torch.randn(Nfwd, Kfwd, device=dev()) / math.sqrt(Nfwd)).to(torch.bfloat16)
+    u = (torch.randn(M, Kfwd, device=dev()) * 1.5).to(torch.bfloat16)
+    got = ops.gemm(dY, W, kind=L.EPI_DACT, act=act, aux=u, w_transposed=True, cta_pair=cta_pair, block_n=block_n)
+    uf = u.float()
+    d = _gelu_grad(uf) if act == 1 else torch.sigmoid(uf) * (1 + uf * (1 - torch.sigmoid(uf)))
+    want = (dY.float() @ W.float()) * d
+    assert rel_l2(got.float(), want) < 4e-3
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("Mtok,Nfwd,Kfwd,splits", [(690, 512, 1280, 1), (1000, 256, 128, 3), (9660, 128, 256, 7), (28, 640, 128, 4)])
+def test_gemm_wgrad_accumulate(ops, L, cta_pair, block_n, Mtok, Nfwd, Kfwd, splits):
+    """dW[N', K'] += dY^T[N', M] X[M, K'] (both operands passed as stored), reduction over tokens split `splits`-way;
+    the token count need not be a multiple of 64 (TMA zero-fills)."""
+    torch.manual_seed(5)
+    dY = torch.randn(Mtok, Nfwd, device=dev()).to(torch.bfloat16)
+    X = torch.randn(Mtok, Kfwd, device=dev()).to(torch.bfloat16)
+    base = torch.randn(Nfwd, Kfwd, device=dev())
+    out = base.clone()
+    ops.gemm(dY, X, kind=L.EPI_ACCUM, out=out, a_transposed=True, w_transposed=True, k_splits=splits,
+             cta_pair=cta_pair, block_n=block_n)
+    want = base + dY.float().t() @ X.float()
+    assert rel_l2(out, want) < 1e-5
+
+
+def test_gemm_forward_keeps_preactivation(ops, L):
+    torch.manual_seed(6)
+    M, N, K = 500, 512, 256
+    A = torch.randn(M, K, device=dev()).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev()) / 16).to(torch.bfloat16)
+    b = torch.randn(N, device=dev())
+    u = torch.zeros(M, N, dtype=torch.bfloat16, device=dev())
+    got = ops.gemm(A, W, act=L.ACT_GELU_ERF, bias=b, aux=u)
+    pre = A.float() @ W.float().t() + b
+    assert rel_l2(u.float(), pre) < 4e-3
+    assert rel_l2(got.float(), torch.nn.functional.gelu(pre)) < 5e-3
+
+
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+def test_gemm_gate_residual_split_k(ops, L, cta_pair, block_n):
+    torch.manual_seed(7)
+    B, Ntok, N, K = 3, 100, 256, 1280
+    M = B * Ntok
+    A = torch.randn(M, K, device=dev()).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev()) / math.sqrt(K)).to(torch.bfloat16)
+    bias, gate = torch.randn(N, device=dev()), torch.randn(B, N, device=dev())
+    x0 = torch.randn(M, N, device=dev())
+    x = x0.clone()
+    ops.gemm(A, W, kind=L.EPI_GATE_RESIDUAL, out=x, bias=bias, gate=gate, gate_batch_stride=N, tokens_per_batch=Ntok,
+             k_splits=5, cta_pair=cta_pair, block_n=block_n)
+    want = x0 + gate.repeat_interleave(Ntok, 0) * (A.float() @ W.float().t() + bias)
+    assert rel_l2(x, want) < 1e-5
