@@ -226,6 +226,30 @@ int jat_profile_begin(jat_ctx* ctx);
 int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts);
 
 /* ----------------------------------------------------------------------------------------------
+ * Backward pass of the DiT block (training step: train_ddp_v3mod2.py:886-922 differentiates
+ * jat_audiosr_v2.py:265-289 with autograd).  The weight / input gradients of every Linear are jat_gemm_bf16 calls
+ * with transposed operands (dgrad: w_transposed; wgrad: a_transposed + w_transposed + JAT_EPI_ACCUM); the
+ * functions below are the HBM-bound pieces in between.  All gradient outputs are ACCUMULATED (+=) except dy/dx-
+ * overwrite modes stated below; f32 unless the name says bf16.
+ *
+ * jat_adaln_bwd: backward of jat_adaln_norm_modulate.  dh bf16 [M, D] (M = B * tokens_per_batch), x the saved f32 input;
+ *   dx (+)= d norm/dx (accumulate != 0 adds to the residual-stream gradient already in dx);
+ *   dshift[b,:] += sum_n dh, dscale[b,:] += sum_n dh * norm(x)[*w]   (rows b * dmod_batch_stride; skipped if scale == NULL);
+ *   dweight[D] += RMSNorm weight gradient (RMSNorm only, may be NULL).
+ * jat_gate_bwd: backward of x += gate_b * y:  dy bf16 = gate_b * dx;  dgate[b,:] += sum_n dx * y;
+ *   if dbias != NULL: dbias[:] += sum_b gate_b * sum_n dx (uses dxsum_scratch f32 [B, D]).
+ * jat_colsum_bf16: out[c] += sum_m a[m, c] (bias gradients).    jat_cast_f32_bf16: elementwise cast.
+ * -------------------------------------------------------------------------------------------- */
+int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* scale, int64_t mod_batch_stride,
+                  const float* weight, int norm_kind, float eps, float* dx, int accumulate, float* dshift, float* dscale,
+                  int64_t dmod_batch_stride, float* dweight, int B, int tokens_per_batch, int D, void* stream);
+int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
+                 void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
+                 int tokens_per_batch, int D, void* stream);
+int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream);
+int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Long-audio chunk plumbing (infer_test_v3m2.py:340-406 chunk loop, :188-233 crossfade_chunks).
  * A track latent[C, total_frames] (row pitch ld) is cut into chunks of `chunk_frames` frames starting every
  * `stride` = chunk_frames - overlap frames.

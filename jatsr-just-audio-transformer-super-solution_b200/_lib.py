@@ -109,6 +109,10 @@ SIGNATURES = {
     "jat_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _vp]),
     "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_cfg_euler_update": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
+    "jat_adaln_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _vp]),
+    "jat_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
+    "jat_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "jat_cast_f32_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "jat_chunk_normalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "jat_crossfade_denorm": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "jat_dit_modulation": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp]),

@@ -12,6 +12,7 @@
 
 #include "../../include/jat_b200.h"
 #include "attention_gqa.cuh"
+#include "backward_elementwise.cuh"
 #include "chunks.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
@@ -42,9 +43,10 @@ struct jat_ctx {
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
                                           "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm",
-                                          "gemm_accum", "gemm_dact"};
+                                          "gemm_accum", "gemm_dact", "adaln_bwd", "gate_bwd", "colsum_cast", "attention_bwd"};
 enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_CHUNKN = 9,
-       TAG_XFADE = 10, TAG_GEMM_ACCUM = 11, TAG_GEMM_DACT = 12, TAG_COUNT = 13 };
+       TAG_XFADE = 10, TAG_GEMM_ACCUM = 11, TAG_GEMM_DACT = 12, TAG_ADALN_BWD = 13,
+       TAG_GATE_BWD = 14, TAG_COLSUM = 15, TAG_ATTN_BWD = 16, TAG_COUNT = 17 };
 
 static thread_local char g_err[512] = "";
 
@@ -441,6 +443,100 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
     cfg_euler_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, x_c, x_u, cfg_scale, t_dt, step,
                                                                        (long long)numel);
     return post_launch(ctx, "cfg_euler_update");
+}
+
+// ------------------------------------------------------------------------------------------------ backward (elementwise)
+template <int NORM>
+static int launch_adaln_bwd(jat_ctx* ctx, const __nv_bfloat16* dh, const float* x, const float* scale, long long bstride,
+                            const float* weight, float eps, float* dx, int accumulate, float* dshift, float* dscale,
+                            long long dbstride, float* dweight, int B, int ntok, int D, cudaStream_t s) {
+    const int nv = (D / 4 + 31) / 32;
+    dim3 grid((ntok + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block(BWD_WARPS * 32);
+    const size_t smem = (size_t)D * sizeof(float);
+    pre_launch(ctx, TAG_ADALN_BWD, s);
+#define JAT_CASE(NV)                                                                                                  \
+    adaln_bwd_kernel<NV, NORM><<<grid, block, smem, s>>>(dh, x, scale, bstride, weight, eps, dx, accumulate, dshift, dscale, \
+                                                         dbstride, dweight, D, ntok)
+    if (nv <= 4) JAT_CASE(4);
+    else if (nv <= 8) JAT_CASE(8);
+    else if (nv <= 10) JAT_CASE(10);
+    else JAT_CASE(16);
+#undef JAT_CASE
+    return post_launch(ctx, "adaln_bwd");
+}
+
+extern "C" int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* scale, int64_t mod_batch_stride,
+                             const float* weight, int norm_kind, float eps, float* dx, int accumulate, float* dshift,
+                             float* dscale, int64_t dmod_batch_stride, float* dweight, int B, int tokens_per_batch, int D,
+                             void* stream) {
+    if (!ctx || !dh_bf16 || !x || !dx) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: null argument");
+    if (scale != nullptr && (!dshift || !dscale)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: dshift/dscale missing");
+    if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_adaln_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
+    if (mod_batch_stride % 4 != 0 || dmod_batch_stride % 4 != 0) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: strides %% 4 != 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (norm_kind == JAT_NORM_LAYERNORM)
+        return launch_adaln_bwd<0>(ctx, (const __nv_bfloat16*)dh_bf16, x, scale, mod_batch_stride, nullptr, eps, dx, accumulate,
+                                   dshift, dscale, dmod_batch_stride, nullptr, B, tokens_per_batch, D, s);
+    if (norm_kind == JAT_NORM_RMSNORM) {
+        if (!weight) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: RMSNorm needs a weight");
+        return launch_adaln_bwd<1>(ctx, (const __nv_bfloat16*)dh_bf16, x, scale, mod_batch_stride, weight, eps, dx, accumulate,
+                                   dshift, dscale, dmod_batch_stride, dweight, B, tokens_per_batch, D, s);
+    }
+    return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: unknown norm_kind %d", norm_kind);
+}
+
+extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
+                            void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
+                            int tokens_per_batch, int D, void* stream) {
+    if (!ctx || !dx || !y_bf16 || !gate || !dy_bf16 || !dgate) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: null argument");
+    if (dbias != nullptr && dxsum_scratch == nullptr) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: dbias needs the [B, D] scratch");
+    if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gate_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* xs = dbias ? dxsum_scratch : nullptr;
+    if (xs) JAT_CUDA(cudaMemsetAsync(xs, 0, (size_t)B * D * sizeof(float), s));
+    const int nv = (D / 4 + 31) / 32;
+    dim3 grid((tokens_per_batch + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block(BWD_WARPS * 32);
+    const size_t smem = (size_t)D * sizeof(float);
+    pre_launch(ctx, TAG_GATE_BWD, s);
+#define JAT_CASE(NV)                                                                                                     \
+    gate_bwd_kernel<NV><<<grid, block, smem, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride,                \
+                                                  (__nv_bfloat16*)dy_bf16, dgate, dmod_batch_stride, xs, D, tokens_per_batch)
+    if (nv <= 4) JAT_CASE(4);
+    else if (nv <= 8) JAT_CASE(8);
+    else if (nv <= 10) JAT_CASE(10);
+    else JAT_CASE(16);
+#undef JAT_CASE
+    JAT_TRY(post_launch(ctx, "gate_bwd"));
+    if (dbias) {
+        pre_launch(ctx, TAG_GATE_BWD, s);
+        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D);
+        return post_launch(ctx, "gate_bias_grad");
+    }
+    return 0;
+}
+
+extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream) {
+    if (!ctx || !a_bf16 || !out) return fail(JAT_ERR_BAD_ARG, "jat_colsum_bf16: null argument");
+    if (M <= 0 || cols <= 0 || cols % 2 != 0 || lda % 2 != 0) return fail(JAT_ERR_BAD_SHAPE, "jat_colsum_bf16: need even cols / lda");
+    int chunks = (M + 63) / 64;
+    const int cap = (ctx->sm_count * 16) / ((cols + 255) / 256) + 1;
+    if (chunks > cap) chunks = cap;
+    dim3 grid((cols + 255) / 256, chunks);
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    colsum_bf16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, (long long)lda, M, cols, out);
+    return post_launch(ctx, "colsum_bf16");
+}
+
+extern "C" int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream) {
+    if (!ctx || !in || !out_bf16 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_cast_f32_bf16: bad argument");
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) != 0)
+        return fail(JAT_ERR_BAD_ARG, "jat_cast_f32_bf16: misaligned");
+    const long long blocks = (n / 4 + 255) / 256 + 1;
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, (long long)n);
+    return post_launch(ctx, "cast_f32_bf16");
 }
 
 // ------------------------------------------------------------------------------------------------ chunks

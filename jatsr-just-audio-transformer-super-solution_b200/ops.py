@@ -151,3 +151,44 @@ def crossfade_denorm(chunks, overlap, total_frames, fade_in=None, fade_out=None,
                                           _p(mean), _p(std), out.data_ptr(), total_frames, out.stride(0),
                                           _stream(chunks.device)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ backward pieces
+def adaln_bwd(dh, x, B, tokens_per_batch, dx, *, scale=None, mod_batch_stride=0, weight=None, norm_kind=L.NORM_LAYERNORM,
+              eps=1e-6, accumulate=True, dshift=None, dscale=None, dmod_batch_stride=0, dweight=None):
+    _chk(dh, torch.bfloat16, "dh")
+    _chk(x, torch.float32, "x")
+    _chk(dx, torch.float32, "dx")
+    D = x.shape[1]
+    L.check(L.load().jat_adaln_bwd(_ctx(x), dh.data_ptr(), x.data_ptr(), _p(scale), mod_batch_stride, _p(weight), norm_kind,
+                                   eps, dx.data_ptr(), int(accumulate), _p(dshift), _p(dscale), dmod_batch_stride,
+                                   _p(dweight), B, tokens_per_batch, D, _stream(x.device)))
+    return dx
+
+
+def gate_bwd(dx, y, gate, B, tokens_per_batch, dgate, *, mod_batch_stride=0, dmod_batch_stride=0, dbias=None, dy=None):
+    _chk(dx, torch.float32, "dx")
+    _chk(y, torch.bfloat16, "y")
+    D = dx.shape[1]
+    if dy is None:
+        dy = torch.empty_like(y)
+    scratch = torch.empty(B, D, dtype=torch.float32, device=dx.device) if dbias is not None else None
+    L.check(L.load().jat_gate_bwd(_ctx(dx), dx.data_ptr(), y.data_ptr(), gate.data_ptr(), mod_batch_stride, dy.data_ptr(),
+                                  dgate.data_ptr(), dmod_batch_stride, _p(scratch), _p(dbias), B, tokens_per_batch, D,
+                                  _stream(dx.device)))
+    return dy
+
+
+def colsum_bf16(a, out):
+    _chk(a, torch.bfloat16, "a")
+    L.check(L.load().jat_colsum_bf16(_ctx(a), a.data_ptr(), a.stride(0), a.shape[0], a.shape[1], out.data_ptr(),
+                                     _stream(a.device)))
+    return out
+
+
+def cast_f32_bf16(x, out=None):
+    _chk(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().jat_cast_f32_bf16(_ctx(x), x.data_ptr(), out.data_ptr(), x.numel(), _stream(x.device)))
+    return out

@@ -363,3 +363,71 @@ def test_gemm_gate_residual_split_k(ops, L, cta_pair, block_n):
              k_splits=5, cta_pair=cta_pair, block_n=block_n)
     want = x0 + gate.repeat_interleave(Ntok, 0) * (A.float() @ W.float().t() + bias)
     assert rel_l2(x, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ backward elementwise
+@pytest.mark.parametrize("norm_kind", [0, 1])
+@pytest.mark.parametrize("D", [512, 1280])
+@pytest.mark.parametrize("mode", ["per_batch", "none"])
+def test_adaln_bwd_matches_autograd(ops, norm_kind, D, mode):
+    torch.manual_seed(21)
+    B, Ntok = 3, 77
+    M = B * Ntok
+    x = (torch.randn(M, D, device=dev()) * 1.3 + 0.2).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(D, device=dev())).requires_grad_(True)
+    shift = (0.3 * torch.randn(B, D, device=dev())).requires_grad_(True)
+    scale = (0.3 * torch.randn(B, D, device=dev())).requires_grad_(True)
+    dh = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+    if norm_kind == 0:
+        y = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    else:
+        y = x * torch.rsqrt((x * x).mean(-1, keepdim=True) + 1e-6) * w
+    h = y
+    if mode == "per_batch":
+        h = y * (1 + scale.repeat_interleave(Ntok, 0)) + shift.repeat_interleave(Ntok, 0)
+    h.backward(dh.float())
+    base = torch.randn(M, D, device=dev())
+    dx = base.clone()
+    dmod = torch.zeros(B, 2 * D, device=dev())
+    dw = torch.zeros(D, device=dev())
+    kw = dict(norm_kind=norm_kind, weight=w.detach() if norm_kind else None, dweight=dw if norm_kind else None)
+    if mode == "per_batch":
+        kw.update(scale=scale.detach(), mod_batch_stride=D, dshift=dmod[:, :D], dscale=dmod[:, D:], dmod_batch_stride=2 * D)
+    ops.adaln_bwd(dh, x.detach(), B, Ntok, dx, accumulate=True, **kw)
+    assert rel_l2(dx - base, x.grad) < 2e-5
+    if mode == "per_batch":
+        assert rel_l2(dmod[:, :D], shift.grad) < 1e-5 and rel_l2(dmod[:, D:], scale.grad) < 1e-5
+    if norm_kind:
+        assert rel_l2(dw, w.grad) < 1e-5
+    dx2 = torch.full_like(base, 7.0)
+    ops.adaln_bwd(dh, x.detach(), B, Ntok, dx2, accumulate=False, **{**kw, **(dict(dshift=torch.zeros(B, D, device=dev()),
+                  dscale=torch.zeros(B, D, device=dev()), dmod_batch_stride=D) if mode == "per_batch" else {})})
+    assert rel_l2(dx2, x.grad) < 2e-5
+
+
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gate_bwd_matches_autograd(ops, with_bias):
+    torch.manual_seed(22)
+    B, Ntok, D = 4, 91, 1280
+    M = B * Ntok
+    dx = torch.randn(M, D, device=dev())
+    y = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+    gate = torch.randn(B, 3 * D, device=dev())[:, D:2 * D]      # a strided view like mod[:, 2D:3D]
+    dgate = torch.zeros(B, D, device=dev())
+    dbias = torch.ones(D, device=dev()) if with_bias else None
+    dy = ops.gate_bwd(dx, y, gate, B, Ntok, dgate, mod_batch_stride=3 * D, dmod_batch_stride=D, dbias=dbias)
+    g = gate.repeat_interleave(Ntok, 0)
+    assert rel_l2(dy.float(), g * dx) < 4e-3
+    assert rel_l2(dgate, (dx * y.float()).view(B, Ntok, D).sum(1)) < 1e-5
+    if with_bias:
+        assert rel_l2(dbias - 1, (g * dx).sum(0)) < 1e-5
+
+
+def test_colsum_and_cast(ops):
+    torch.manual_seed(23)
+    a = torch.randn(9660, 512, device=dev()).to(torch.bfloat16)
+    out = torch.ones(512, device=dev())
+    ops.colsum_bf16(a, out)
+    assert rel_l2(out - 1, a.float().sum(0)) < 1e-5
+    x = torch.randn(28 * 7680 + 3, device=dev())
+    assert torch.equal(ops.cast_f32_bf16(x), x.to(torch.bfloat16))
