@@ -135,10 +135,20 @@ int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64
  * on the packed projection buffer written by the QKV_ROPE GEMM:
  *   qkv bf16 [B * N, (Hq + 2*Hkv) * 64] = [ Q heads | K heads | V heads ],   out bf16 [B * N, Hq*64].
  * No mask, bidirectional. K/V of one KV head are staged in shared memory once per CTA and reused
- * by the Hq/Hkv query heads of the group. head_dim must be 64; N <= 512.
+ * by the Hq/Hkv query heads of the group. head_dim must be 64; N <= 352.
+ * lse_or_null: optional f32 [B, Hq, N] output, log2(sum_j 2^(s_ij * log2(e) / 8)) per query row, kept by the training
+ * forward for jat_gqa_attention_bwd.
  * -------------------------------------------------------------------------------------------- */
-int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, int B, int N, int Hq, int Hkv,
-                          int head_dim, void* stream);
+int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, float* lse_or_null, int B, int N, int Hq,
+                          int Hkv, int head_dim, void* stream);
+
+/* Backward of jat_gqa_attention_fwd (dropout 0).  d_out / out bf16 [B*N, Hq*64] (gradient of, and the saved, forward
+ * output), lse from the forward call.  Writes dqkv bf16 [B*N, (Hq+2Hkv)*64] = gradient w.r.t. the PRE-RoPE q | k | v
+ * projections (the RoPE rotation of the QKV epilogue is transposed inside).  Scratch (caller-owned):
+ * dsum_scratch f32 [B, Hq, N], dq_acc_scratch f32 [B*N, Hq*64].  rope_cos/sin: the forward's tables. */
+int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv_bf16, const void* d_out_bf16, const void* out_bf16, const float* lse,
+                          float* dsum_scratch, float* dq_acc_scratch, void* dqkv_bf16, const float* rope_cos,
+                          const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Fused sampler update (infer_test_v3m2.py:161-179): CFG combine + x-prediction -> velocity + Euler.

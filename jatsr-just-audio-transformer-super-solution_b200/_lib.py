@@ -107,7 +107,8 @@ SIGNATURES = {
     "jat_patchify_cast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "jat_timestep_features": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "jat_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _vp]),
-    "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "jat_gqa_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_cfg_euler_update": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
     "jat_adaln_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _vp]),
     "jat_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),

@@ -12,6 +12,7 @@
 
 #include "../../include/jat_b200.h"
 #include "attention_gqa.cuh"
+#include "attention_bwd.cuh"
 #include "backward_elementwise.cuh"
 #include "chunks.cuh"
 #include "elementwise.cuh"
@@ -596,7 +597,7 @@ static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv
     return post_launch(ctx, "gqa_attention_fwd");
 }
 
-extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, int B, int N, int Hq, int Hkv,
+extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq, int Hkv,
                                      int head_dim, void* stream) {
     if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
@@ -608,6 +609,7 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, i
     AttnParams p = {};
     p.B = B; p.N = N; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
     p.out = (__nv_bfloat16*)out;
+    p.lse = lse;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.trace = ctx->att_trace;
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
@@ -621,6 +623,52 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, i
     if (N <= 192) return launch_attention<96>(ctx, tq, qkv, rows, cols, p, grid, s);
     if (N <= 256) return launch_attention<128>(ctx, tq, qkv, rows, cols, p, grid, s);
     return launch_attention<176>(ctx, tq, qkv, rows, cols, p, grid, s);
+}
+
+extern "C" int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv, const void* d_out, const void* out, const float* lse,
+                                     float* dsum_scratch, float* dq_acc_scratch, void* dqkv, const float* rope_cos,
+                                     const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, void* stream) {
+    if (!ctx || !qkv || !d_out || !out || !lse || !dsum_scratch || !dq_acc_scratch || !dqkv || !rope_cos || !rope_sin)
+        return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: null argument");
+    if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_bwd: head_dim must be 64 (got %d)", head_dim);
+    if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_bwd: bad B/N/heads");
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t rows = (uint64_t)B * N, qcols = (uint64_t)Hq * ATT_HD, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
+    JAT_CUDA(cudaMemsetAsync(dq_acc_scratch, 0, rows * qcols * sizeof(float), s));
+    {
+        const long long n = (long long)rows * Hq;
+        pre_launch(ctx, TAG_ATTN_BWD, s);
+        attn_bwd_rowdot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)d_out, (const __nv_bfloat16*)out,
+                                                                         dsum_scratch, B, N, Hq);
+        JAT_TRY(post_launch(ctx, "attn_bwd_rowdot"));
+    }
+    CUtensorMap tqkv, tdo, tdq;
+    JAT_TRY(make_tmap(ctx, &tqkv, qkv, rows, cols, cols, ATTB_TILE));
+    JAT_TRY(make_tmap(ctx, &tdo, d_out, rows, qcols, qcols, ATTB_TILE));
+    JAT_TRY(make_tmap(ctx, &tdq, dq_acc_scratch, rows, qcols, qcols, ATTB_TILE, /*f32=*/true));
+    AttnBwdParams p = {};
+    p.B = B; p.N = N; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
+    p.lse = lse; p.dsum = dsum_scratch; p.dqkv = (__nv_bfloat16*)dqkv;
+    p.rope_cos = rope_cos; p.rope_sin = rope_sin;
+    p.scale = 0.125f;
+    p.scale_log2e = 0.125f * 1.4426950408889634f;
+    static bool configured = false;
+    if (!configured) {
+        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTB_SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((N + ATTB_TILE - 1) / ATTB_TILE, Hkv, B);
+    pre_launch(ctx, TAG_ATTN_BWD, s);
+    gqa_attention_bwd_kernel<<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+    JAT_TRY(post_launch(ctx, "gqa_attention_bwd"));
+    {
+        const long long n = (long long)rows * Hq * 8;
+        pre_launch(ctx, TAG_ATTN_BWD, s);
+        attn_bwd_dq_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dq_acc_scratch, (__nv_bfloat16*)dqkv, rope_cos,
+                                                                              rope_sin, B, N, Hq, Hkv);
+        return post_launch(ctx, "attn_bwd_dq_finalize");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ DiT forward plan
@@ -677,7 +725,7 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
         e.kind = JAT_EPI_QKV_ROPE; e.out = ws->qkv; e.ldo = QKV; e.tokens_per_batch = N;
         e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (w->n_q_heads + w->n_kv_heads) * 64;
         JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
-        JAT_TRY(jat_gqa_attention_fwd(ctx, ws->qkv, ws->attn, B, N, w->n_q_heads, w->n_kv_heads, 64, stream));
+        JAT_TRY(jat_gqa_attention_fwd(ctx, ws->qkv, ws->attn, nullptr, B, N, w->n_q_heads, w->n_kv_heads, 64, stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
         e.gate = m + 2 * D; e.gate_batch_stride = mod_batch_stride;

@@ -1,0 +1,364 @@
+// GQA attention BACKWARD on tcgen05 / TMEM (autograd of GroupedQueryAttention.forward, jat_audiosr_v2.py:141-164,
+// dropout = 0).  Inputs: the packed projections qkv (RoPE already applied to Q and K), the forward output O, its
+// gradient dO and the per-row log-sum-exp kept by the forward kernel.  With P = softmax(Q K^T / 8):
+//     dV = P^T dO      dP = dO V^T      dS = P * (dP - D) / 8,  D_i = sum_d dO_id O_id      dQ = dS K      dK = dS^T Q
+// One CTA owns 128 KEYS of one (batch item, KV head) and walks over every query tile of the G query heads that
+// share that KV head, so dK / dV accumulate in tensor memory for the whole kernel (no atomics), S^T and dP^T are
+// recomputed per tile (nothing of size N x N is ever stored), and only dQ -- whose reduction runs over the key
+// tiles, i.e. over CTAs -- leaves through TMA reduce-add into an f32 accumulator.
+//
+//   tensor memory:  S^T [0,128)   dP^T [128,256)   dV [256,320)   dK [320,384)   dQ [384,448)      (fp32 columns)
+//   per (head, q-tile) iteration:
+//     MMA  S^T  = K  Q^T        (M = keys 128, N = queries 128, K = 64; both operands K-major)
+//     MMA  dP^T = V  dO^T
+//     warps 4-7 (thread = key row): P^T = 2^(S^T log2e/8 - lse_q),  dS^T = P^T (dP^T - D_q) / 8  -> bf16 smem tiles
+//     MMA  dV  += P^T  dO       (A K-major from smem; B = dO tile consumed MN-major as stored)
+//     MMA  dK  += dS^T Q        (B = Q tile MN-major)
+//     MMA  dQ   = dS   K        (A = the same dS^T tile read MN-major, B = K tile MN-major) -> TMA reduce-add
+//   epilogue: dV -> bf16,  dK -> inverse RoPE -> bf16, written into the [M, (Hq+2Hkv)*64] gradient of qkv.
+#pragma once
+#include <cuda.h>
+#include "attention_gqa.cuh"
+
+namespace jat {
+
+constexpr int ATTB_THREADS = 256;
+constexpr int ATTB_TILE = 128;
+constexpr int ATTB_TILE_BYTES = ATTB_TILE * 128;  // [128 rows x 64 bf16]
+constexpr int ATTB_SMEM_BYTES = 2 * ATTB_TILE_BYTES          // K, V
+                                + 4 * ATTB_TILE_BYTES        // Q, dO double-buffered
+                                + 4 * ATTB_TILE_BYTES        // P^T, dS^T ([128 x 128] bf16 = 2 blocks each)
+                                + 2 * ATTB_TILE_BYTES        // dQ staging [128 x 64] f32 = 2 boxes
+                                + 2 * 2 * ATTB_TILE * 4      // lse, D per query (double-buffered)
+                                + 256 + 1024;
+
+struct AttnBwdParams {
+    int B, N, Hq, Hkv, G;
+    const float* lse;   // [B, Hq, N] log2-domain
+    const float* dsum;  // [B, Hq, N] D_i = rowsum(dO * O)
+    __nv_bfloat16* dqkv;  // [B*N, (Hq + 2 Hkv) * 64]: this kernel writes the K and V column ranges
+    const float* rope_cos;  // [max_pos, 64]
+    const float* rope_sin;
+    float scale_log2e, scale;
+};
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(ATTB_THREADS, 1)
+gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                         const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + ATTB_TILE_BYTES;
+    uint8_t* sQ = sV + ATTB_TILE_BYTES;          // 2 stages
+    uint8_t* sdO = sQ + 2 * ATTB_TILE_BYTES;     // 2 stages
+    uint8_t* sPT = sdO + 2 * ATTB_TILE_BYTES;    // 2 blocks of 64 queries
+    uint8_t* sdST = sPT + 2 * ATTB_TILE_BYTES;   // 2 blocks of 64 queries
+    uint8_t* sdQ = sdST + 2 * ATTB_TILE_BYTES;   // 2 boxes of 32 f32 columns
+    float* s_lse = reinterpret_cast<float*>(sdQ + 2 * ATTB_TILE_BYTES);  // [2][128]
+    float* s_dsum = s_lse + 2 * ATTB_TILE;                                // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dsum + 2 * ATTB_TILE);
+    uint64_t* bar_kv = bars;
+    uint64_t* bar_q_full = bars + 1;    // [2]
+    uint64_t* bar_q_empty = bars + 3;   // [2]
+    uint64_t* bar_sp_full = bars + 5;   // S^T, dP^T retired
+    uint64_t* bar_pds_full = bars + 6;  // P^T, dS^T written (128 compute threads)
+    uint64_t* bar_mma2_done = bars + 7; // dV, dK, dQ MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int QT = (p.N + ATTB_TILE - 1) / ATTB_TILE;
+    const int iters = p.G * QT;
+    const int row_b = b * p.N;  // first token row of this batch item
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(bar_kv, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_q_full[i], 1); mbar_init(&bar_q_empty[i], 1); }
+        mbar_init(bar_sp_full, 1);
+        mbar_init(bar_pds_full, 128);
+        mbar_init(bar_mma2_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_qkv);
+            tma_prefetch_desc(&tmap_do);
+            tma_prefetch_desc(&tmap_dq);
+            mbar_expect_tx(bar_kv, 2 * ATTB_TILE_BYTES);
+            tma_load_2d(sK, &tmap_qkv, bar_kv, (p.Hq + g) * ATT_HD, row_b + kt * ATTB_TILE);
+            tma_load_2d(sV, &tmap_qkv, bar_kv, (p.Hq + p.Hkv + g) * ATT_HD, row_b + kt * ATTB_TILE);
+            for (int it = 0; it < iters; ++it) {
+                const int st = it & 1;
+                mbar_wait(&bar_q_empty[st], (uint32_t)(((it >> 1) & 1) ^ 1));
+                const int h = g * p.G + it / QT, qt = it % QT;
+                mbar_expect_tx(&bar_q_full[st], 2 * ATTB_TILE_BYTES);
+                tma_load_2d(sQ + st * ATTB_TILE_BYTES, &tmap_qkv, &bar_q_full[st], h * ATT_HD, row_b + qt * ATTB_TILE);
+                tma_load_2d(sdO + st * ATTB_TILE_BYTES, &tmap_do, &bar_q_full[st], h * ATT_HD, row_b + qt * ATTB_TILE);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
+            constexpr uint32_t idesc_kv = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK: A K-major, B MN-major
+            constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 1, 1);   // dQ: both MN-major
+            const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sK));
+            const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV));
+            const uint64_t k_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sK), ATTB_TILE_BYTES);
+            const uint64_t dst_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sdST), ATTB_TILE_BYTES);
+            auto issue_first = [&](int it) {  // S^T = K Q^T, dP^T = V dO^T
+                const int st = it & 1;
+                mbar_wait(&bar_q_full[st], (uint32_t)((it >> 1) & 1));
+                tc_fence_after();
+                const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ + st * ATTB_TILE_BYTES));
+                const uint64_t do_desc = umma_smem_desc_sw128(smem_u32(sdO + st * ATTB_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_ST, k_desc + 2 * k, q_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_DPT, v_desc + 2 * k, do_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
+                umma_commit(bar_sp_full);
+            };
+            mbar_wait(bar_kv, 0);
+            issue_first(0);
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int st = it & 1;
+                mbar_wait(bar_pds_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                const uint64_t q_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sQ + st * ATTB_TILE_BYTES), ATTB_TILE_BYTES);
+                const uint64_t do_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sdO + st * ATTB_TILE_BYTES), ATTB_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {  // reduction over the 128 queries of the tile, 16 per step
+                    const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
+                    umma_bf16_ss<1>(tmem_base + COL_DV, umma_smem_desc_sw128(smem_u32(sPT)) + a_off,
+                                    do_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv, (uint32_t)((it != 0) | (ks != 0)));
+                }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
+                    umma_bf16_ss<1>(tmem_base + COL_DK, umma_smem_desc_sw128(smem_u32(sdST)) + a_off,
+                                    q_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv, (uint32_t)((it != 0) | (ks != 0)));
+                }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)  // reduction over the 128 keys of this CTA
+                    umma_bf16_ss<1>(tmem_base + COL_DQ, dst_desc_mn + (uint64_t)(ks * (2048 >> 4)),
+                                    k_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_dq, (uint32_t)(ks != 0));
+                umma_commit(bar_mma2_done);
+                umma_commit(&bar_q_empty[st]);
+                if (it + 1 < iters) issue_first(it + 1);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ compute warps: thread = key row
+        const int r = (warp & 3) * 32 + lane;
+        const int t = threadIdx.x - 128;  // 0..127, == r
+        const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int key = kt * ATTB_TILE + r;
+        const bool key_ok = key < p.N;
+        const uint32_t rx = (uint32_t)(r & 7);
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t sPT_row = smem_u32(sPT) + row_off, sdST_row = smem_u32(sdST) + row_off;
+        const uint32_t sdQ_row = smem_u32(sdQ) + row_off;
+
+        auto dq_epilogue = [&](int it) {  // dQ tile of iteration `it`: TMEM -> f32 smem boxes -> TMA reduce-add
+            const int h = g * p.G + it / QT, qt = it % QT;
+            if (t == 0) tma_store_wait_read<0>();  // the previous reduce-add has drained the staging tile
+            named_bar(1, 128);
+#pragma unroll
+            for (int bx = 0; bx < 2; ++bx) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + COL_DQ + bx * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t addr = sdQ_row + (uint32_t)bx * ATTB_TILE_BYTES + ((((uint32_t)c) ^ rx) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                 "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            named_bar(1, 128);
+            if (t == 0) {
+                tma_reduce_add_2d(&tmap_dq, sdQ, h * ATT_HD, row_b + qt * ATTB_TILE);
+                tma_reduce_add_2d(&tmap_dq, sdQ + ATTB_TILE_BYTES, h * ATT_HD + 32, row_b + qt * ATTB_TILE);
+                tma_store_commit();
+            }
+        };
+
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            const int h = g * p.G + it / QT, qt = it % QT;
+            const int slot = it & 1;
+            {   // per-query statistics of this tile (queries past the batch item's N tokens get lse = +inf -> P = 0)
+                const int q = qt * ATTB_TILE + t;
+                const bool q_ok = q < p.N;
+                const long long idx = ((long long)b * p.Hq + h) * p.N + q;
+                s_lse[slot * ATTB_TILE + t] = q_ok ? __ldg(p.lse + idx) : INFINITY;
+                s_dsum[slot * ATTB_TILE + t] = q_ok ? __ldg(p.dsum + idx) : 0.0f;
+            }
+            if (it > 0) {
+                mbar_wait(bar_mma2_done, (uint32_t)((it - 1) & 1));  // P^T / dS^T tiles free, dQ(it-1) complete
+                tc_fence_after();
+                dq_epilogue(it - 1);   // (its named barriers also publish s_lse / s_dsum)
+            } else {
+                named_bar(1, 128);
+            }
+            mbar_wait(bar_sp_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            const float* lse_t = s_lse + slot * ATTB_TILE;
+            const float* ds_t = s_dsum + slot * ATTB_TILE;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {  // 32 queries at a time
+                uint32_t sv[32], dv[32];
+                tmem_ld_32x32(t_row + COL_ST + c * 32, sv);
+                tmem_ld_32x32(t_row + COL_DPT + c * 32, dv);
+                tmem_ld_wait();
+                uint32_t pp[16], dd[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = 0.f, p1 = 0.f;
+                    if (key_ok) {
+                        p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2e, -lse_t[c * 32 + j]));
+                        p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2e, -lse_t[c * 32 + j + 1]));
+                    }
+                    const float d0 = p0 * (__uint_as_float(dv[j]) - ds_t[c * 32 + j]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(dv[j + 1]) - ds_t[c * 32 + j + 1]) * p.scale;
+                    pp[j >> 1] = pack_bf16(p0, p1);
+                    dd[j >> 1] = pack_bf16(d0, d1);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {  // 32 queries = 64 bytes = 4 x 16 B chunks of block (c >> 1)
+                    const uint32_t off = (uint32_t)(c >> 1) * ATTB_TILE_BYTES + (((uint32_t)((c & 1) * 4 + i) ^ rx) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sPT_row + off), "r"(pp[4 * i]), "r"(pp[4 * i + 1]),
+                                 "r"(pp[4 * i + 2]), "r"(pp[4 * i + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sdST_row + off), "r"(dd[4 * i]), "r"(dd[4 * i + 1]),
+                                 "r"(dd[4 * i + 2]), "r"(dd[4 * i + 3]) : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_pds_full);
+        }
+        mbar_wait(bar_mma2_done, (uint32_t)((iters - 1) & 1));
+        tc_fence_after();
+        dq_epilogue(iters - 1);
+        // ---- dV, dK of this key row (dK through the transpose of the RoPE rotation, jat_audiosr_v2.py:70-91)
+        {   // (tcgen05.ld is warp-collective: every lane loads, only rows that hold a real key store)
+            __nv_bfloat16* orow = p.dqkv + (long long)(row_b + (key_ok ? key : 0)) * ((p.Hq + 2 * p.Hkv) * ATT_HD);
+            uint32_t lo[32], hi[32];
+            tmem_ld_32x32(t_row + COL_DV, lo);
+            tmem_ld_32x32(t_row + COL_DV + 32, hi);
+            tmem_ld_wait();
+            __nv_bfloat16* ov = orow + (p.Hq + p.Hkv + g) * ATT_HD;
+            if (key_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    *reinterpret_cast<uint4*>(ov + j) = make_uint4(
+                        pack_bf16(__uint_as_float(lo[j]), __uint_as_float(lo[j + 1])), pack_bf16(__uint_as_float(lo[j + 2]), __uint_as_float(lo[j + 3])),
+                        pack_bf16(__uint_as_float(lo[j + 4]), __uint_as_float(lo[j + 5])), pack_bf16(__uint_as_float(lo[j + 6]), __uint_as_float(lo[j + 7])));
+                    *reinterpret_cast<uint4*>(ov + 32 + j) = make_uint4(
+                        pack_bf16(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), pack_bf16(__uint_as_float(hi[j + 2]), __uint_as_float(hi[j + 3])),
+                        pack_bf16(__uint_as_float(hi[j + 4]), __uint_as_float(hi[j + 5])), pack_bf16(__uint_as_float(hi[j + 6]), __uint_as_float(hi[j + 7])));
+                }
+            }
+            tmem_ld_32x32(t_row + COL_DK, lo);
+            tmem_ld_32x32(t_row + COL_DK + 32, hi);
+            tmem_ld_wait();
+            if (key_ok) {
+                const float* cosr = p.rope_cos + (long long)key * 64;
+                const float* sinr = p.rope_sin + (long long)key * 64;
+                __nv_bfloat16* ok = orow + (p.Hq + g) * ATT_HD;
+                float ra[32], rb[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {  // forward: lo' = a c - b s, hi' = b c + a s  ->  da = glo c + ghi s, db = ghi c - glo s
+                    const float c = __ldg(cosr + j), s = __ldg(sinr + j);
+                    const float glo = __uint_as_float(lo[j]), ghi = __uint_as_float(hi[j]);
+                    ra[j] = glo * c + ghi * s;
+                    rb[j] = ghi * c - glo * s;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    *reinterpret_cast<uint4*>(ok + j) = make_uint4(pack_bf16(ra[j], ra[j + 1]), pack_bf16(ra[j + 2], ra[j + 3]),
+                                                                   pack_bf16(ra[j + 4], ra[j + 5]), pack_bf16(ra[j + 6], ra[j + 7]));
+                    *reinterpret_cast<uint4*>(ok + 32 + j) = make_uint4(pack_bf16(rb[j], rb[j + 1]), pack_bf16(rb[j + 2], rb[j + 3]),
+                                                                        pack_bf16(rb[j + 4], rb[j + 5]), pack_bf16(rb[j + 6], rb[j + 7]));
+                }
+            }
+        }
+        if (t == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+// D[b, h, n] = sum_d dO[m, h*64 + d] * O[m, h*64 + d]   (one thread per (token row, head))
+__global__ void attn_bwd_rowdot_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
+                                       float* __restrict__ dsum, int B, int N, int Hq) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N * Hq) return;
+    const int h = (int)(i % Hq);
+    const long long m = i / Hq;
+    const uint4* a = reinterpret_cast<const uint4*>(dO + m * (Hq * 64) + h * 64);
+    const uint4* c = reinterpret_cast<const uint4*>(O + m * (Hq * 64) + h * 64);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint4 x = __ldg(a + k), y = __ldg(c + k);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            s += __uint_as_float(xs[q] << 16) * __uint_as_float(ys[q] << 16) +
+                 __uint_as_float(xs[q] & 0xffff0000u) * __uint_as_float(ys[q] & 0xffff0000u);
+    }
+    const int bidx = (int)(m / N), n = (int)(m % N);
+    dsum[((long long)bidx * Hq + h) * N + n] = s;
+}
+
+// dq (bf16, into the Q column range of dqkv) = inverse-RoPE(dQ accumulator f32 [M, Hq*64]); one thread per
+// (row, head, 4 column pairs)
+__global__ void attn_bwd_dq_finalize_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
+                                            const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int B,
+                                            int N, int Hq, int Hkv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N * Hq * 8) return;
+    const int j = (int)(i & 7) * 4;
+    const long long mh = i >> 3;
+    const int h = (int)(mh % Hq);
+    const long long m = mh / Hq;
+    const int pos = (int)(m % N);
+    const float4 glo = *reinterpret_cast<const float4*>(dq_acc + m * (Hq * 64) + h * 64 + j);
+    const float4 ghi = *reinterpret_cast<const float4*>(dq_acc + m * (Hq * 64) + h * 64 + 32 + j);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(rope_cos + (long long)pos * 64 + j));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(rope_sin + (long long)pos * 64 + j));
+    __nv_bfloat16* o = dqkv + m * ((Hq + 2 * Hkv) * 64) + h * 64;
+    *reinterpret_cast<uint2*>(o + j) = make_uint2(pack_bf16(glo.x * c.x + ghi.x * s.x, glo.y * c.y + ghi.y * s.y),
+                                                  pack_bf16(glo.z * c.z + ghi.z * s.z, glo.w * c.w + ghi.w * s.w));
+    *reinterpret_cast<uint2*>(o + 32 + j) = make_uint2(pack_bf16(ghi.x * c.x - glo.x * s.x, ghi.y * c.y - glo.y * s.y),
+                                                       pack_bf16(ghi.z * c.z - glo.z * s.z, ghi.w * c.w - glo.w * s.w));
+}
+
+}  // namespace jat

@@ -62,6 +62,7 @@ struct AttCfg {
 struct AttnParams {
     int B, N, Hq, Hkv, G;
     __nv_bfloat16* out;
+    float* lse;         // optional f32 [B, Hq, N]: log2-domain log-sum-exp of the scaled scores (kept for the backward pass)
     float scale_log2e;  // (1/sqrt(64)) * log2(e)
     long long* trace;   // debug: per-event clock64 timestamps of CTA (0,0,0), or NULL
 };
@@ -245,8 +246,11 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const float2 sb = stats[(h & 1) * 2 * ATT_BQ + ATT_BQ + r];
             const float mx = fmaxf(sa.x, sb.x);  // half A always holds at least one real key -> finite
             const float wa0 = ex2_approx(sa.x - mx), wb0 = ex2_approx(sb.x - mx);  // 2^(-inf) = 0 for an all-padding half
-            const float inv = 1.0f / (wa0 * sa.y + wb0 * sb.y);
+            const float den = wa0 * sa.y + wb0 * sb.y;
+            const float inv = 1.0f / den;
             const float wa = wa0 * inv, wb = wb0 * inv;
+            if (p.lse != nullptr && row_ok)
+                p.lse[((long long)b * p.Hq + g * p.G + h) * p.N + qt * ATT_BQ + r] = mx + __log2f(den);
             __nv_bfloat16* o = out_row + (long long)h * ATT_HD;
 #pragma unroll
             for (int c = 0; c < ATT_HD / 16; ++c) {

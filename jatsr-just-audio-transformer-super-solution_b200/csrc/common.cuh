@@ -8,7 +8,7 @@
 
 #ifndef JAT_SPIN_LIMIT
 // Bounded spin on every mbarrier wait: a protocol bug traps instead of hanging the GPU box.
-#define JAT_SPIN_LIMIT (1u << 26)
+#define JAT_SPIN_LIMIT (1u << 22)
 #endif
 
 namespace jat {

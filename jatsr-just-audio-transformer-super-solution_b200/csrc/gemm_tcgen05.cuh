@@ -337,6 +337,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
                               r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
                         if constexpr (EPI == EPI_GATE_RESIDUAL) {
+                            if (p.aux != nullptr && row_ok)  // training forward keeps y = acc + bias (bf16) for the gate gradient
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.aux)) +
+                                                          (long long)m * p.ld_aux + n0 + j) =
+                                    make_uint2(pack_bf16(r0, r1), pack_bf16(r2, r3));
                             const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
                             r0 *= g4.x; r1 *= g4.y; r2 *= g4.z; r3 *= g4.w;
                         } else if constexpr (EPI == EPI_BIAS_ACT) {

@@ -103,12 +103,13 @@ def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, b
     return out
 
 
-def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None):
+def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None):
+    """lse: optional f32 [B, Hq, N] output (log2-domain log-sum-exp per query row, for the backward pass)."""
     _chk(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (B * N, (Hq + 2 * Hkv) * head_dim)
     if out is None:
         out = torch.empty(B * N, Hq * head_dim, dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().jat_gqa_attention_fwd(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), B, N, Hq, Hkv, head_dim,
+    L.check(L.load().jat_gqa_attention_fwd(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, Hq, Hkv, head_dim,
                                            _stream(qkv.device)))
     return out
 
@@ -192,3 +193,18 @@ def cast_f32_bf16(x, out=None):
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     L.check(L.load().jat_cast_f32_bf16(_ctx(x), x.data_ptr(), out.data_ptr(), x.numel(), _stream(x.device)))
     return out
+
+
+def gqa_attention_bwd(qkv, d_out, out, lse, rope_cos, rope_sin, B, N, Hq, Hkv, head_dim=64, dqkv=None):
+    """Gradient w.r.t. the pre-RoPE packed q|k|v projections, bf16 [B*N, (Hq+2Hkv)*64]."""
+    for t, n in ((qkv, "qkv"), (d_out, "d_out"), (out, "out")):
+        _chk(t, torch.bfloat16, n)
+    _chk(lse, torch.float32, "lse")
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    dsum = torch.empty(B, Hq, N, dtype=torch.float32, device=qkv.device)
+    dq_acc = torch.empty(B * N, Hq * head_dim, dtype=torch.float32, device=qkv.device)
+    L.check(L.load().jat_gqa_attention_bwd(_ctx(qkv), qkv.data_ptr(), d_out.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                                           dsum.data_ptr(), dq_acc.data_ptr(), dqkv.data_ptr(), rope_cos.data_ptr(),
+                                           rope_sin.data_ptr(), B, N, Hq, Hkv, head_dim, _stream(qkv.device)))
+    return dqkv

@@ -431,3 +431,46 @@ def test_colsum_and_cast(ops):
     assert rel_l2(out - 1, a.float().sum(0)) < 1e-5
     x = torch.randn(28 * 7680 + 3, device=dev())
     assert torch.equal(ops.cast_f32_bf16(x), x.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ attention backward
+def _rope_tables(npos):
+    inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=dev()).float() / 64))
+    f = torch.outer(torch.arange(npos, device=dev()).float(), inv)
+    e = torch.cat([f, f], -1)
+    return e.cos().contiguous(), e.sin().contiguous()
+
+
+def _rope(x, cos, sin):  # x [B, N, H, 64]
+    x1, x2 = x[..., :32], x[..., 32:]
+    return x * cos[None, :, None, :] + torch.cat([-x2, x1], -1) * sin[None, :, None, :]
+
+
+@pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 4, 2), (2, 256, 2, 2), (1, 300, 5, 1)])
+def test_gqa_attention_bwd_matches_autograd(ops, B, N, Hq, Hkv):
+    """dqkv (w.r.t. the PRE-RoPE projections) vs torch autograd through RoPE + repeat_interleave + softmax attention."""
+    torch.manual_seed(31)
+    G = Hq // Hkv
+    cos, sin = _rope_tables(N)
+    raw = (torch.randn(B, N, Hq + 2 * Hkv, 64, device=dev())).to(torch.bfloat16).float().requires_grad_(True)
+    q = _rope(raw[:, :, :Hq], cos, sin)
+    k = _rope(raw[:, :, Hq:Hq + Hkv], cos, sin)
+    v = raw[:, :, Hq + Hkv:]
+    # the kernels see bf16 RoPE'd projections (what the QKV GEMM epilogue stores)
+    qkv = torch.cat([q, k, v], 2).detach().reshape(B * N, -1).to(torch.bfloat16)
+    lse = torch.empty(B, Hq, N, device=dev())
+    out = ops.gqa_attention_fwd(qkv, B, N, Hq, Hkv, lse=lse)
+    d_out = torch.randn(B * N, Hq * 64, device=dev()).to(torch.bfloat16)
+    got = ops.gqa_attention_bwd(qkv, d_out, out, lse, cos, sin, B, N, Hq, Hkv).float().view(B, N, Hq + 2 * Hkv, 64)
+
+    kk = k.repeat_interleave(G, dim=2)
+    vv = v.repeat_interleave(G, dim=2)
+    s = torch.einsum("bnhd,bmhd->bhnm", q, kk) / 8.0
+    want_lse = torch.logsumexp(s, -1) * math.log2(math.e)
+    assert (lse - want_lse.detach()).abs().max() < 2e-2
+    o = torch.einsum("bhnm,bmhd->bnhd", torch.softmax(s, -1), vv).reshape(B * N, Hq * 64)
+    o.backward(d_out.float())
+    want = raw.grad
+    for name, sl in (("dq", slice(0, Hq)), ("dk", slice(Hq, Hq + Hkv)), ("dv", slice(Hq + Hkv, Hq + 2 * Hkv))):
+        err = rel_l2(got[:, :, sl], want[:, :, sl])
+        assert err < 1.5e-2, (name, err)
