@@ -222,6 +222,60 @@ int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit
                            int xt_batch, const float* x_cond, int cond_batch, const float* mod,
                            int64_t mod_batch_stride, float* out, int B, int T, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Training step (train_ddp_v3mod2.py:886 forward, :922 backward; dropout / DropPath must be 0 -- the reference's own
+ * gradient semantics are only defined then).  `jat_dit_forward_train` = JaT_AudioSR_V2/V3.forward with
+ * per-sample t, keeping in `saved` what the backward needs; `jat_dit_backward` = autograd of that forward: given
+ * d_out = dL/d(out) f32 [B, C, T] it ACCUMULATES (+=) f32 parameter gradients into `grads`, a jat_dit_weights whose
+ * pointers address f32 buffers with exactly the shapes of the (bf16 / f32) weights they mirror.  No gradient is
+ * produced for x_t / x_cond / t (the reference never differentiates them).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct jat_dit_saved {
+    /* per-block slabs: [depth, ...] */
+    float* x_in;  /* f32  [depth, M, hidden]  residual stream entering the block (norm1 input) */
+    float* x_mid; /* f32  [depth, M, hidden]  after the attention branch (norm2 input) */
+    void* h1;     /* bf16 [depth, M, hidden] */
+    void* qkv;    /* bf16 [depth, M, (Hq+2Hkv)*64] */
+    void* attn;   /* bf16 [depth, M, hidden] */
+    float* lse;   /* f32  [depth, B, Hq, N] */
+    void* y1;     /* bf16 [depth, M, hidden]  out_proj output (before the gate) */
+    void* h2;     /* bf16 [depth, M, hidden] */
+    void* u;      /* bf16 [depth, M, mlp_hidden]  mlp.0 pre-activation */
+    void* mact;   /* bf16 [depth, M, mlp_hidden]  gelu(u) */
+    void* y2;     /* bf16 [depth, M, hidden]  mlp.3 output (before the gate) */
+    void* pe_u;   /* bf16 [M, bottleneck]  patch_embed.proj.0 pre-activation */
+    void* t_u1;   /* bf16 [B, hidden]  t_embedder.1 pre-activation */
+    void* t_u2;   /* bf16 [B, hidden]  t_emb (input of the adaLN SiLU) */
+} jat_dit_saved;
+
+typedef struct jat_dit_bwd_scratch {
+    float* dx;       /* f32  [M, hidden]  residual-stream gradient */
+    void* dy;        /* bf16 [M, hidden] */
+    void* dh;        /* bf16 [M, hidden] */
+    void* da;        /* bf16 [M, hidden] */
+    void* du;        /* bf16 [M, mlp_hidden] */
+    void* dqkv;      /* bf16 [M, (Hq+2Hkv)*64] */
+    float* dsum;     /* f32  [B, Hq, N] */
+    float* dq_acc;   /* f32  [M, Hq*64] */
+    float* dmod;     /* f32  [B, depth*6*hidden] */
+    void* dmod_bf16; /* bf16 [B, depth*6*hidden] */
+    float* dxsum;    /* f32  [B, hidden] */
+    void* dout_p;    /* bf16 [M, C*P] */
+    void* dpe;       /* bf16 [M, bottleneck] */
+    void* dt_a;      /* bf16 [B, hidden] */
+    void* dt_b;      /* bf16 [B, hidden] */
+} jat_dit_bwd_scratch;
+
+int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
+                          const float* x_t, const float* x_cond, const float* t, float* out, int B, int T, void* stream);
+int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
+                     const jat_dit_bwd_scratch* scratch, const jat_dit_weights* grads, const float* d_out, int B, int T,
+                     void* stream);
+
+/* Single-source patchify + cast (the transpose of the un-patchify epilogue, used on d_out):
+ * out bf16 [B*N, C*P], out[b*N + n, c*P + p] = x[b, c, n*P + p] (0 past T). */
+int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int C, int T, int P, void* stream);
+
 /* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
 int64_t jat_launch_count(const jat_ctx* ctx);
 

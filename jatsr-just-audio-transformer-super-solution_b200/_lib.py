@@ -90,6 +90,16 @@ class DitWorkspace(C.Structure):
     ]
 
 
+class DitSaved(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x_in", "x_mid", "h1", "qkv", "attn", "lse", "y1", "h2", "u", "mact", "y2",
+                                          "pe_u", "t_u1", "t_u2")]
+
+
+class DitBwdScratch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dh", "da", "du", "dqkv", "dsum", "dq_acc", "dmod", "dmod_bf16",
+                                          "dxsum", "dout_p", "dpe", "dt_a", "dt_b")]
+
+
 # name -> (restype, argtypes); every symbol include/jat_b200.h declares
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
@@ -116,6 +126,11 @@ SIGNATURES = {
     "jat_cast_f32_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "jat_chunk_normalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "jat_crossfade_denorm": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "jat_patchify_single": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "jat_dit_forward_train": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved), _vp, _vp, _vp,
+                                    _vp, _i, _i, _vp]),
+    "jat_dit_backward": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved),
+                               C.POINTER(DitBwdScratch), C.POINTER(DitWeights), _vp, _i, _i, _vp]),
     "jat_dit_modulation": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp]),
     "jat_dit_forward_tokens": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp, _i, _vp,
                                      _i64, _vp, _i, _i, _vp]),

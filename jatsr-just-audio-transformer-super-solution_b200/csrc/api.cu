@@ -420,8 +420,19 @@ extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, c
     dim3 grid((N + PATCH_TN - 1) / PATCH_TN, 2 * C / PATCH_TC, B);
     pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
     patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, xt_batch, x_cond, cond_batch,
-                                                                 (__nv_bfloat16*)out_bf16, C, T, N);
+                                                                 (__nv_bfloat16*)out_bf16, C, T, N, 2 * C * 4);
     return post_launch(ctx, "patchify_cast");
+}
+
+extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int C, int T, int P, void* stream) {
+    if (!ctx || !x || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_patchify_single: null argument");
+    if (P != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_single: patch_len must be 4 (got %d)", P);
+    if (B <= 0 || C <= 0 || T <= 0 || C % PATCH_TC != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_single: bad sizes");
+    const int N = (T + P - 1) / P;
+    dim3 grid((N + PATCH_TN - 1) / PATCH_TN, C / PATCH_TC, B);
+    pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
+    patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, nullptr, 0, (__nv_bfloat16*)out_bf16, C, T, N, C * 4);
+    return post_launch(ctx, "patchify_single");
 }
 
 extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf16, int B, int D, void* stream) {
@@ -748,5 +759,185 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
     memset(&e, 0, sizeof(e));
     e.kind = JAT_EPI_UNPATCHIFY; e.out = out; e.bias = w->final_b; e.tokens_per_batch = N; e.patch_len = P; e.t_out = T;
     JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->final_w, D, M, C * P, D, &e, -1, 0, stream));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ training step
+// Training-mode forward (dropout / DropPath = 0): the same kernels as jat_dit_forward_tokens, but every activation
+// the backward pass needs is kept in `sv` (per-block slabs, leading dimension = depth) instead of being overwritten.
+static jat_gemm_epilogue epi_plain(int kind, void* out, int64_t ldo) {
+    jat_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.kind = kind; e.out = out; e.ldo = ldo; e.out_dtype = JAT_DTYPE_BF16;
+    return e;
+}
+static char* at(void* base, int64_t index, int64_t elems, int64_t esz) { return (char*)base + index * elems * esz; }
+
+extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
+                                     const jat_dit_saved* sv, const float* x_t, const float* x_cond, const float* t,
+                                     float* out, int B, int T, void* stream) {
+    if (!ctx || !w || !ws || !sv || !x_t || !x_cond || !t || !out) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_train: null argument");
+    const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
+    const int N = (T + P - 1) / P;
+    if (N > w->max_len) return fail(JAT_ERR_SEQ_TOO_LONG, "Sequence length %d exceeds max_len %d", N, w->max_len);
+    if (w->head_dim != 64) return fail(JAT_ERR_BAD_SHAPE, "head_dim must be 64");
+    const int M = B * N, Hq = w->n_q_heads, Hkv = w->n_kv_heads;
+    const int QKV = (Hq + 2 * Hkv) * 64, KIN = 2 * C * P, NM = w->depth * 6 * D;
+    cudaStream_t s = (cudaStream_t)stream;
+    jat_gemm_epilogue e;
+
+    // ---- timestep path with the pre-activations kept (t_embedder + adaLN_modulation of every block)
+    JAT_TRY(jat_timestep_features(ctx, t, ws->t_feat, B, D, stream));
+    e = epi_bias_act(w->te_b1, ws->t_hid, D, JAT_ACT_SILU, JAT_DTYPE_BF16); e.aux = sv->t_u1; e.ld_aux = D;
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_feat, D, w->te_w1, D, B, D, D, &e, -1, 0, stream));
+    e = epi_bias_act(w->te_b2, ws->t_act, D, JAT_ACT_SILU, JAT_DTYPE_BF16); e.aux = sv->t_u2; e.ld_aux = D;
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_hid, D, w->te_w2, D, B, D, D, &e, -1, 0, stream));
+    e = epi_bias_act(w->ada_b, ws->mod, NM, JAT_ACT_NONE, JAT_DTYPE_F32);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->t_act, D, w->ada_w, D, B, NM, D, &e, -1, 0, stream));
+
+    // ---- patch embed
+    JAT_TRY(jat_patchify_cast(ctx, x_t, B, x_cond, B, ws->patches, B, C, T, P, stream));
+    e = epi_bias_act(w->pe_b1, ws->pe_hid, BD, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16); e.aux = sv->pe_u; e.ld_aux = BD;
+    JAT_TRY(jat_gemm_bf16(ctx, ws->patches, KIN, w->pe_w1, KIN, M, BD, KIN, &e, -1, 0, stream));
+    e = epi_bias_act(w->pe_b2, ws->x, D, JAT_ACT_NONE, JAT_DTYPE_F32);
+    JAT_TRY(jat_gemm_bf16(ctx, ws->pe_hid, BD, w->pe_w2, BD, M, D, BD, &e, -1, 0, stream));
+
+    const int64_t MD = (int64_t)M * D;
+    for (int i = 0; i < w->depth; ++i) {
+        const float* m = ws->mod + (int64_t)i * 6 * D;
+        void* h1 = at(sv->h1, i, MD, 2);
+        void* qkv = at(sv->qkv, i, (int64_t)M * QKV, 2);
+        void* attn = at(sv->attn, i, MD, 2);
+        void* h2 = at(sv->h2, i, MD, 2);
+        void* mact = at(sv->mact, i, (int64_t)M * F, 2);
+        JAT_CUDA(cudaMemcpyAsync(at(sv->x_in, i, MD, 4), ws->x, MD * 4, cudaMemcpyDeviceToDevice, s));
+        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, h1, m, m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind,
+                                        w->norm_eps, M, D, N, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_QKV_ROPE; e.out = qkv; e.ldo = QKV; e.tokens_per_batch = N;
+        e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (Hq + Hkv) * 64;
+        JAT_TRY(jat_gemm_bf16(ctx, h1, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
+        JAT_TRY(jat_gqa_attention_fwd(ctx, qkv, attn, (float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), B, N, Hq, Hkv, 64, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
+        e.gate = m + 2 * D; e.gate_batch_stride = NM; e.aux = at(sv->y1, i, MD, 2); e.ld_aux = D;
+        JAT_TRY(jat_gemm_bf16(ctx, attn, D, w->wo[i], D, M, D, D, &e, -1, 0, stream));
+
+        JAT_CUDA(cudaMemcpyAsync(at(sv->x_mid, i, MD, 4), ws->x, MD * 4, cudaMemcpyDeviceToDevice, s));
+        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, h2, m + 3 * D, m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
+                                        w->norm_kind, w->norm_eps, M, D, N, stream));
+        e = epi_bias_act(w->b1[i], mact, F, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
+        e.aux = at(sv->u, i, (int64_t)M * F, 2); e.ld_aux = F;
+        JAT_TRY(jat_gemm_bf16(ctx, h2, D, w->w1[i], D, M, F, D, &e, -1, 0, stream));
+        memset(&e, 0, sizeof(e));
+        e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N; e.bias = w->b2[i];
+        e.gate = m + 5 * D; e.gate_batch_stride = NM; e.aux = at(sv->y2, i, MD, 2); e.ld_aux = D;
+        JAT_TRY(jat_gemm_bf16(ctx, mact, F, w->w2[i], F, M, D, F, &e, -1, 0, stream));
+    }
+    // final layer: ws->x (input of the final norm) and ws->h (its output) stay valid until the backward pass
+    JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, ws->h, nullptr, nullptr, 0, w->final_norm_w, w->norm_kind, w->norm_eps, M,
+                                    D, N, stream));
+    memset(&e, 0, sizeof(e));
+    e.kind = JAT_EPI_UNPATCHIFY; e.out = out; e.bias = w->final_b; e.tokens_per_batch = N; e.patch_len = P; e.t_out = T;
+    JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->final_w, D, M, C * P, D, &e, -1, 0, stream));
+    return 0;
+}
+
+// weight gradient  g[Nout, Kin] += dY^T[Nout, Mtok] X[Mtok, Kin]  (both operands as stored), reduction split so that
+// the grid holds a few waves of work items
+static int wgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* X, int64_t ld_x, float* g, int Nout, int Kin,
+                 int Mtok, void* stream) {
+    jat_gemm_epilogue e = epi_plain(JAT_EPI_ACCUM, g, Kin);
+    e.a_transposed = 1; e.w_transposed = 1;
+    const int bn = (Kin % 256 == 0) ? 256 : 128;
+    const long long tiles = (long long)((Nout + 255) / 256) * (Kin / bn);
+    long long want = (4LL * (ctx->sm_count / 2) + tiles - 1) / tiles;
+    const int kblocks = (Mtok + GEMM_BK - 1) / GEMM_BK;
+    if (want > 16) want = 16;
+    if (want > kblocks) want = kblocks;
+    e.k_splits = (int)(want < 1 ? 1 : want);
+    return jat_gemm_bf16(ctx, dY, ld_dy, X, ld_x, Nout, Kin, Mtok, &e, -1, 0, stream);
+}
+// input gradient  dX[Mtok, Kin] = dY[Mtok, Nout] W[Nout, Kin]  (W as stored), optional * act'(u)
+static int dgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* W, int Kin, int Nout, int Mtok, void* dX, int act,
+                 const void* u, void* stream) {
+    jat_gemm_epilogue e = epi_plain(act == JAT_ACT_NONE ? JAT_EPI_BIAS_ACT : JAT_EPI_DACT, dX, Kin);
+    e.act = act; e.w_transposed = 1; e.aux = const_cast<void*>(u); e.ld_aux = Kin;
+    return jat_gemm_bf16(ctx, dY, ld_dy, W, Kin, Mtok, Kin, Nout, &e, -1, 0, stream);
+}
+
+extern "C" int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* sv,
+                                const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, const float* d_out, int B, int T,
+                                void* stream) {
+    if (!ctx || !w || !ws || !sv || !sc || !gr || !d_out) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward: null argument");
+    const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
+    const int N = (T + P - 1) / P, M = B * N, Hq = w->n_q_heads, Hkv = w->n_kv_heads;
+    const int QKV = (Hq + 2 * Hkv) * 64, KIN = 2 * C * P, NM = w->depth * 6 * D, CP = C * P;
+    const int64_t MD = (int64_t)M * D;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool rms = w->norm_kind == JAT_NORM_RMSNORM;
+    JAT_CUDA(cudaMemsetAsync(sc->dmod, 0, (size_t)B * NM * sizeof(float), s));
+
+    // ---- final layer: out = unpatchify(hf Wf^T + bf), hf = norm(x_L)
+    JAT_TRY(jat_patchify_single(ctx, d_out, sc->dout_p, B, C, T, P, stream));
+    JAT_TRY(wgrad(ctx, sc->dout_p, CP, ws->h, D, (float*)gr->final_w, CP, D, M, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dout_p, CP, M, CP, (float*)gr->final_b, stream));
+    JAT_TRY(dgrad(ctx, sc->dout_p, CP, w->final_w, D, CP, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    JAT_TRY(jat_adaln_bwd(ctx, sc->dh, ws->x, nullptr, 0, w->final_norm_w, w->norm_kind, w->norm_eps, sc->dx, 0, nullptr,
+                          nullptr, 0, rms ? (float*)gr->final_norm_w : nullptr, B, N, D, stream));
+
+    for (int i = w->depth - 1; i >= 0; --i) {
+        const float* m = ws->mod + (int64_t)i * 6 * D;
+        float* dm = sc->dmod + (int64_t)i * 6 * D;
+        const void* h1 = at(sv->h1, i, MD, 2);
+        const void* qkv = at(sv->qkv, i, (int64_t)M * QKV, 2);
+        const void* attn = at(sv->attn, i, MD, 2);
+        const void* h2 = at(sv->h2, i, MD, 2);
+        const void* u = at(sv->u, i, (int64_t)M * F, 2);
+        const void* mact = at(sv->mact, i, (int64_t)M * F, 2);
+        // ---- MLP branch: x2 = x1 + gate_mlp * (gelu(h2 W1^T + b1) W2^T + b2)
+        JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, NM, sc->dxsum,
+                             (float*)gr->b2[i], B, N, D, stream));
+        JAT_TRY(wgrad(ctx, sc->dy, D, mact, F, (float*)gr->w2[i], D, F, M, stream));
+        JAT_TRY(dgrad(ctx, sc->dy, D, w->w2[i], F, D, M, sc->du, JAT_ACT_GELU_ERF, u, stream));
+        JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
+        JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
+        JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+        JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), m + 4 * D, NM,
+                              w->norm2_w ? w->norm2_w[i] : nullptr, w->norm_kind, w->norm_eps, sc->dx, 1, dm + 3 * D, dm + 4 * D,
+                              NM, rms ? (float*)gr->norm2_w[i] : nullptr, B, N, D, stream));
+        // ---- attention branch: x1 = x + gate_msa * (attn(h1) Wo^T)
+        JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, NM, nullptr, nullptr, B, N, D,
+                             stream));
+        JAT_TRY(wgrad(ctx, sc->dy, D, attn, D, (float*)gr->wo[i], D, D, M, stream));
+        JAT_TRY(dgrad(ctx, sc->dy, D, w->wo[i], D, D, M, sc->da, JAT_ACT_NONE, nullptr, stream));
+        JAT_TRY(jat_gqa_attention_bwd(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), sc->dsum,
+                                      sc->dq_acc, sc->dqkv, w->rope_cos, w->rope_sin, B, N, Hq, Hkv, 64, stream));
+        JAT_TRY(wgrad(ctx, sc->dqkv, QKV, h1, D, (float*)gr->wqkv[i], QKV, D, M, stream));
+        JAT_TRY(dgrad(ctx, sc->dqkv, QKV, w->wqkv[i], D, QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+        JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,
+                              w->norm_kind, w->norm_eps, sc->dx, 1, dm, dm + D, NM, rms ? (float*)gr->norm1_w[i] : nullptr, B, N, D,
+                              stream));
+    }
+
+    // ---- patch embed: x0 = gelu(patches W1^T + b1) W2^T + b2   (no gradient flows to the inputs)
+    JAT_TRY(jat_cast_f32_bf16(ctx, sc->dx, sc->dy, MD, stream));
+    JAT_TRY(wgrad(ctx, sc->dy, D, ws->pe_hid, BD, (float*)gr->pe_w2, D, BD, M, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dy, D, M, D, (float*)gr->pe_b2, stream));
+    JAT_TRY(dgrad(ctx, sc->dy, D, w->pe_w2, BD, D, M, sc->dpe, JAT_ACT_GELU_ERF, sv->pe_u, stream));
+    JAT_TRY(wgrad(ctx, sc->dpe, BD, ws->patches, KIN, (float*)gr->pe_w1, BD, KIN, M, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dpe, BD, M, BD, (float*)gr->pe_b1, stream));
+
+    // ---- timestep path: mod = silu(t_emb) Wada^T + bada,  t_emb = silu(feat W1^T + b1) W2^T + b2
+    JAT_TRY(jat_cast_f32_bf16(ctx, sc->dmod, sc->dmod_bf16, (int64_t)B * NM, stream));
+    JAT_TRY(wgrad(ctx, sc->dmod_bf16, NM, ws->t_act, D, (float*)gr->ada_w, NM, D, B, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dmod_bf16, NM, B, NM, (float*)gr->ada_b, stream));
+    JAT_TRY(dgrad(ctx, sc->dmod_bf16, NM, w->ada_w, D, NM, B, sc->dt_a, JAT_ACT_SILU, sv->t_u2, stream));  // d t_emb (pre-SiLU)
+    JAT_TRY(wgrad(ctx, sc->dt_a, D, ws->t_hid, D, (float*)gr->te_w2, D, D, B, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dt_a, D, B, D, (float*)gr->te_b2, stream));
+    JAT_TRY(dgrad(ctx, sc->dt_a, D, w->te_w2, D, D, B, sc->dt_b, JAT_ACT_SILU, sv->t_u1, stream));
+    JAT_TRY(wgrad(ctx, sc->dt_b, D, ws->t_feat, D, (float*)gr->te_w1, D, D, B, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dt_b, D, B, D, (float*)gr->te_b1, stream));
     return 0;
 }

@@ -98,7 +98,7 @@ constexpr int PATCH_ROW = PATCH_TN * 4 + 4;  // padded smem row (floats)
 
 __global__ void __launch_bounds__(256)
 patchify_cast_kernel(const float* __restrict__ x_t, int xt_batch, const float* __restrict__ x_cond, int cond_batch,
-                     __nv_bfloat16* __restrict__ out, int C, int T, int N) {
+                     __nv_bfloat16* __restrict__ out, int C, int T, int N, int K) {
     __shared__ __align__(16) float tile[PATCH_TC][PATCH_ROW];
     const int n0 = blockIdx.x * PATCH_TN;
     const int c0 = blockIdx.y * PATCH_TC;  // in [0, 2C)
@@ -121,7 +121,6 @@ patchify_cast_kernel(const float* __restrict__ x_t, int xt_batch, const float* _
         }
     }
     __syncthreads();
-    const int K = 2 * C * 4;
 #pragma unroll
     for (int nn = warp; nn < PATCH_TN; nn += 8) {
         const int n = n0 + nn;

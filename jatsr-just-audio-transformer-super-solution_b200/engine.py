@@ -90,6 +90,102 @@ class PackedWeights:
         return device != self.device or self._versions(model) != self.versions
 
 
+class PackedGrads:
+    """f32 gradient buffers in the packed layout of PackedWeights (q|k|v rows concatenated, adaLN stacked) plus the
+    map back to the model's parameters: every parameter's gradient is a contiguous row-slice VIEW of a packed buffer,
+    so `jat_dit_backward` writes straight into what autograd hands to the optimizer / DDP."""
+
+    def __init__(self, model, device):
+        D, depth = model.hidden_size, len(model.blocks)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        like = lambda p: z(*p.shape)
+        attn0 = model.blocks[0].attn
+        qd, kd = attn0.q_proj.out_features, attn0.k_proj.out_features
+        k = self.keep = {}
+        pe, te = model.patch_embed.proj, model.t_embedder
+        k["pe_w1"], k["pe_b1"], k["pe_w2"], k["pe_b2"] = like(pe[0].weight), like(pe[0].bias), like(pe[2].weight), like(pe[2].bias)
+        k["te_w1"], k["te_b1"], k["te_w2"], k["te_b2"] = like(te[1].weight), like(te[1].bias), like(te[3].weight), like(te[3].bias)
+        k["ada_w"], k["ada_b"] = z(depth * 6 * D, D), z(depth * 6 * D)
+        k["wqkv"] = [z(qd + 2 * kd, D) for _ in range(depth)]
+        k["wo"] = [like(b.attn.out_proj.weight) for b in model.blocks]
+        k["w1"] = [like(b.mlp[0].weight) for b in model.blocks]
+        k["b1"] = [like(b.mlp[0].bias) for b in model.blocks]
+        k["w2"] = [like(b.mlp[3].weight) for b in model.blocks]
+        k["b2"] = [like(b.mlp[3].bias) for b in model.blocks]
+        rms = model.norm_kind == L.NORM_RMSNORM
+        if rms:
+            k["n1"] = [z(D) for _ in range(depth)]
+            k["n2"] = [z(D) for _ in range(depth)]
+            k["nf"] = z(D)
+        k["final_w"], k["final_b"] = like(model.final_layer[1].weight), like(model.final_layer[1].bias)
+        # parameter -> gradient view
+        g = self.by_param = {}
+        g[pe[0].weight], g[pe[0].bias], g[pe[2].weight], g[pe[2].bias] = k["pe_w1"], k["pe_b1"], k["pe_w2"], k["pe_b2"]
+        g[te[1].weight], g[te[1].bias], g[te[3].weight], g[te[3].bias] = k["te_w1"], k["te_b1"], k["te_w2"], k["te_b2"]
+        for i, b in enumerate(model.blocks):
+            g[b.adaLN_modulation[1].weight] = k["ada_w"][i * 6 * D:(i + 1) * 6 * D]
+            g[b.adaLN_modulation[1].bias] = k["ada_b"][i * 6 * D:(i + 1) * 6 * D]
+            g[b.attn.q_proj.weight] = k["wqkv"][i][:qd]
+            g[b.attn.k_proj.weight] = k["wqkv"][i][qd:qd + kd]
+            g[b.attn.v_proj.weight] = k["wqkv"][i][qd + kd:]
+            g[b.attn.out_proj.weight] = k["wo"][i]
+            g[b.mlp[0].weight], g[b.mlp[0].bias], g[b.mlp[3].weight], g[b.mlp[3].bias] = k["w1"][i], k["b1"][i], k["w2"][i], k["b2"][i]
+            if rms:
+                g[b.norm1.weight], g[b.norm2.weight] = k["n1"][i], k["n2"][i]
+        if rms:
+            g[model.final_layer[0].weight] = k["nf"]
+        g[model.final_layer[1].weight], g[model.final_layer[1].bias] = k["final_w"], k["final_b"]
+        self.arrays = {n: _ptr_array(k[n]) for n in ("wqkv", "wo", "w1", "b1", "w2", "b2")}
+        if rms:
+            self.arrays["n1"], self.arrays["n2"] = _ptr_array(k["n1"]), _ptr_array(k["n2"])
+        w = self.struct = L.DitWeights()
+        p = lambda t: t.data_ptr()
+        w.pe_w1, w.pe_b1, w.pe_w2, w.pe_b2 = p(k["pe_w1"]), p(k["pe_b1"]), p(k["pe_w2"]), p(k["pe_b2"])
+        w.te_w1, w.te_b1, w.te_w2, w.te_b2 = p(k["te_w1"]), p(k["te_b1"]), p(k["te_w2"]), p(k["te_b2"])
+        w.ada_w, w.ada_b = p(k["ada_w"]), p(k["ada_b"])
+        cast = lambda a: C.cast(a, C.POINTER(C.c_void_p))
+        w.wqkv, w.wo = cast(self.arrays["wqkv"]), cast(self.arrays["wo"])
+        w.w1, w.b1, w.w2, w.b2 = (cast(self.arrays[n]) for n in ("w1", "b1", "w2", "b2"))
+        if rms:
+            w.norm1_w, w.norm2_w, w.final_norm_w = cast(self.arrays["n1"]), cast(self.arrays["n2"]), p(k["nf"])
+        w.final_w, w.final_b = p(k["final_w"]), p(k["final_b"])
+
+    def zero_(self):
+        for v in self.keep.values():
+            for t in (v if isinstance(v, list) else [v]):
+                t.zero_()
+
+
+class TrainBuffers:
+    """Saved activations + backward scratch for one (B, T) training problem."""
+
+    def __init__(self, model, B, T, device):
+        D, depth = model.hidden_size, len(model.blocks)
+        P, Cc = model.patch_len, model.input_channels
+        N = (T + P - 1) // P
+        M = B * N
+        attn0 = model.blocks[0].attn
+        Hq, Hkv = attn0.num_q_heads, attn0.num_kv_heads
+        qkv = (Hq + 2 * Hkv) * attn0.head_dim
+        F = model.blocks[0].mlp[0].out_features
+        BD = model.patch_embed.proj[0].out_features
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=device)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.saved = dict(x_in=f32(depth, M, D), x_mid=f32(depth, M, D), h1=bf(depth, M, D), qkv=bf(depth, M, qkv),
+                          attn=bf(depth, M, D), lse=f32(depth, B, Hq, N), y1=bf(depth, M, D), h2=bf(depth, M, D),
+                          u=bf(depth, M, F), mact=bf(depth, M, F), y2=bf(depth, M, D), pe_u=bf(M, BD), t_u1=bf(B, D),
+                          t_u2=bf(B, D))
+        NM = depth * 6 * D
+        self.scratch = dict(dx=f32(M, D), dy=bf(M, D), dh=bf(M, D), da=bf(M, D), du=bf(M, F), dqkv=bf(M, qkv),
+                            dsum=f32(B, Hq, N), dq_acc=f32(M, Hq * attn0.head_dim), dmod=f32(B, NM), dmod_bf16=bf(B, NM),
+                            dxsum=f32(B, D), dout_p=bf(M, Cc * P), dpe=bf(M, BD), dt_a=bf(B, D), dt_b=bf(B, D))
+        self.sv, self.sc = L.DitSaved(), L.DitBwdScratch()
+        for k_, v in self.saved.items():
+            setattr(self.sv, k_, v.data_ptr())
+        for k_, v in self.scratch.items():
+            setattr(self.sc, k_, v.data_ptr())
+
+
 class Workspace:
     """Activation buffers for one (B, T, Bt) problem size."""
 
@@ -168,6 +264,48 @@ class Engine:
             raise ValueError(lib.jat_last_error().decode())
         L.check(code)
         return out
+
+    # ------------------------------------------------------------------------------------ training step
+    def train_buffers(self, B, T, device):
+        key = (B, T, device)
+        tb = getattr(self, "_train", {}).get(key)
+        if tb is None:
+            self._train = {key: TrainBuffers(self.model, B, T, device)}
+            tb = self._train[key]
+        return tb
+
+    def grads(self, device):
+        if getattr(self, "_grads", None) is None or self._grads.keep["pe_b1"].device != device:
+            self._grads = PackedGrads(self.model, device)
+        return self._grads
+
+    def forward_train(self, x_t, t, x_cond):
+        B, Cc, T = x_t.shape
+        dev = x_t.device
+        lib, ctx = L.load(), L.context(self._dev_index(dev))
+        pw = self.weights(dev)
+        ws = self.workspace(B, T, B, dev)
+        tb = self.train_buffers(B, T, dev)
+        out = torch.empty(B, Cc, T, dtype=torch.float32, device=dev)
+        code = lib.jat_dit_forward_train(ctx, C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), x_t.data_ptr(),
+                                         x_cond.data_ptr(), t.data_ptr(), out.data_ptr(), B, T,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+        if code == L.ERR_SEQ_TOO_LONG:
+            raise ValueError(lib.jat_last_error().decode())
+        L.check(code)
+        return out
+
+    def backward(self, d_out, B, T):
+        """d_out f32 [B, C, T] -> {parameter: f32 gradient view}; the saved activations of the last forward_train
+        with the same (B, T) are consumed."""
+        dev = d_out.device
+        lib, ctx = L.load(), L.context(self._dev_index(dev))
+        pw, ws, tb = self.weights(dev), self.workspace(B, T, B, dev), self.train_buffers(B, T, dev)
+        gr = self.grads(dev)
+        gr.zero_()
+        L.check(lib.jat_dit_backward(ctx, C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), C.byref(tb.sc),
+                                     C.byref(gr.struct), d_out.data_ptr(), B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return gr.by_param
 
     def forward(self, x_t, t, x_cond, keep_blocks=False):
         """Plain model forward: per-sample t (jat_audiosr_v2.py:399-448)."""

@@ -19,6 +19,27 @@ from . import _lib as L
 from .engine import Engine
 
 
+class _DiTFunction(torch.autograd.Function):
+    """autograd node of the whole forward: forward = jat_dit_forward_train, backward = jat_dit_backward.  The
+    parameters are inputs of the node (so AdamW / GradScaler / clip_grad_norm_ / DDP hooks see ordinary .grad
+    tensors); x_t, t and x_cond get no gradient (the reference never differentiates them)."""
+
+    @staticmethod
+    def forward(ctx, model, x_t, t, x_cond, *params):
+        ctx.model, ctx.shape = model, (x_t.shape[0], x_t.shape[2])
+        ctx.n_params = len(params)
+        return model._engine.forward_train(x_t, t, x_cond)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        model = ctx.model
+        B, T = ctx.shape
+        by_param = model._engine.backward(d_out.float().contiguous(), B, T)
+        # fresh tensors: autograd / DDP may keep or accumulate into what we return, the packed buffers are reused
+        grads = tuple(by_param[p].clone() if p.requires_grad else None for p in model.parameters())
+        return (None, None, None, None) + grads
+
+
 class TimeEmbedding(nn.Module):
     """Parameter-free placeholder at t_embedder.0 (jat_audiosr_v2.py:170-190); computed by
     `jat_timestep_features`."""
@@ -140,8 +161,8 @@ class _JaTBase(nn.Module):
         if t.dim() != 1 or t.shape[0] != x_t.shape[0]:
             raise ValueError("t must be [B]")
         if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError("train-mode Dropout/DropPath is not implemented by the CUDA path yet; "
-                                      "call model.eval()")
+            raise NotImplementedError("train-mode Dropout / DropPath is not implemented by the CUDA path yet: build the "
+                                      "model with dropout=0.0, drop_path_rate=0.0 (or call model.eval())")
         N = (x_t.shape[-1] + self.patch_len - 1) // self.patch_len
         if N > self.max_len:
             raise ValueError(f"Sequence length {N} exceeds max_len {self.max_len}")
@@ -149,7 +170,11 @@ class _JaTBase(nn.Module):
     def forward(self, x_t, t, x_cond):
         """x_t, x_cond [B, C, T]; t [B] in [0, 1] -> x_pred [B, C, T] (jat_audiosr_v2.py:399-448)."""
         self._check_inputs(x_t, t, x_cond)
-        out = self._engine.forward(x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous())
+        xt, tt, xc = x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous()
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            out = _DiTFunction.apply(self, xt, tt, xc, *self.parameters())
+        else:
+            out = self._engine.forward(xt, tt, xc)
         if torch.is_autocast_enabled():
             out = out.to(torch.get_autocast_gpu_dtype())
         return out
