@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the K timed steps from one captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
+                    help="sample = headline CFG denoise step (configs[2]); train = DDP training step (configs[3])")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -163,6 +165,8 @@ def main():
 
     if a.impl == "reference":
         return reference_arm(a, K, W, rank, world, config)
+    if a.mode == "train":
+        return train_main(a, K, W, rank, world, local)
 
     import torch
     import jat_b200
@@ -288,6 +292,106 @@ def main():
                 "step_tflops": round(step_flops / (ms / K) / 1e9, 1),
                 "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),
                 "graph": bool(a.graph)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_main(a, K, W, rank, world, local):
+    """BASELINE configs[3]: v3mod2 training step, batch 28 per GPU, x-prediction MSE flow-matching loss
+    (train_ddp_v3mod2.py:842-930 without the perceptual losses / logging), DDP over NCCL for N > 1.
+    One step = zero_grad + forward + loss + backward (+ gradient all-reduce) + clip_grad_norm_ + AdamW + weight re-pack."""
+    import torch
+    import jat_b200
+    from jat_b200 import _lib as L
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", init_method="env://")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = dict(CFG, dropout=0.0, drop_path_rate=0.0)
+    cls = jat_b200.JaT_AudioSR_V2 if a.norm == "layernorm" else jat_b200.JaT_AudioSR_V3
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = cls(**cfg)
+    g = torch.Generator(device=dev).manual_seed(1)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "adaLN_modulation.1" in name or name.startswith("final_layer.1"):
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) * 0.02)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.1, fused=True)   # train_ddp_v3mod2.py:709
+    gd = torch.Generator(device=dev).manual_seed(100 + rank)
+    hr = torch.randn(B, C, T, generator=gd, device=dev)
+    lr = torch.randn(B, C, T, generator=gd, device=dev)
+
+    def step():
+        u = torch.rand(B, generator=gd, device=dev)                                   # U-shaped t, :449-457
+        t = torch.where(u < 0.5, (2 * u).sqrt() / 2, 1 - (2 * (1 - u)).sqrt() / 2)
+        noise = torch.randn(B, C, T, generator=gd, device=dev)
+        z_t = t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * noise                    # :881-883
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(net(z_t, t, lr), hr)                      # :886-889
+        loss.backward()                                                               # :922 (+ DDP all-reduce)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                       # :926
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    ctx, lib = L.context(local), L.load()
+    l0 = lib.jat_launch_count(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = lib.jat_launch_count(ctx) - l0
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    assert torch.isfinite(loss).all()
+    L.profile_begin(local)
+    pk = min(K, 3)
+    for _ in range(pk):
+        step()
+    prof = L.profile_end(local)
+    pkz = peaks()
+    tot = sum(v[0] for v in prof.values())
+    kernels = {n: {"ms_per_step": round(v[0] / pk, 3), "launches_per_step": v[1] // pk, "share_of_kernel_time": round(v[0] / tot, 4)}
+               for n, v in prof.items()}
+    # algorithmic FLOPs (SURVEY.md 8d): forward 1023.85 MFLOP/token, backward = 2x forward, no recompute counted
+    N = (T + 3) // 4
+    step_flops = 3 * 1023.85e6 * B * N
+    if rank == 0:
+        value = world * K / (ms / 1e3)
+        line = {"metric": "v3mod2 DDP training steps/sec (batch 28 per GPU, x-prediction MSE flow-matching loss)",
+                "value": round(value, 3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "configs[3]: v3mod2 DiT 1280/28/20Q/4KV training step, batch 28 x [1024,1378] per GPU "
+                                       "(9660 token rows), AdamW(fused) + clip_grad_norm, MSE x-prediction loss",
+                           "norm": a.norm, "dropout": 0.0, "drop_path": 0.0,
+                           "note": "train-mode Dropout/DropPath are not implemented by the CUDA path yet (reference: 0.1 / 0.05)",
+                           "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU"},
+                "clocks": clk, "gpu_launches": int(launches), "loss": round(float(loss.item()), 5),
+                "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),
+                "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),
+                "kernels": kernels, "kernel_ms_per_step": round(tot / pk, 2)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

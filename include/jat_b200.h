@@ -257,13 +257,15 @@ typedef struct jat_dit_bwd_scratch {
     void* dqkv;      /* bf16 [M, (Hq+2Hkv)*64] */
     float* dsum;     /* f32  [B, Hq, N] */
     float* dq_acc;   /* f32  [M, Hq*64] */
-    float* dmod;     /* f32  [B, depth*6*hidden] */
-    void* dmod_bf16; /* bf16 [B, depth*6*hidden] */
+    float* dmod;     /* f32  [depth, B, 6*hidden]  (block-major) */
+    void* dmod_bf16; /* bf16 [depth, B, 6*hidden] */
     float* dxsum;    /* f32  [B, hidden] */
     void* dout_p;    /* bf16 [M, C*P] */
     void* dpe;       /* bf16 [M, bottleneck] */
     void* dt_a;      /* bf16 [B, hidden] */
     void* dt_b;      /* bf16 [B, hidden] */
+    float* dt_acc;   /* f32  [B, hidden]  gradient w.r.t. silu(t_emb), summed over the blocks */
+    float* rowstats; /* f32  [M, 2]  row mean / rstd scratch of jat_adaln_bwd */
 } jat_dit_bwd_scratch;
 
 int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
@@ -271,6 +273,18 @@ int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_
 int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
                      const jat_dit_bwd_scratch* scratch, const jat_dit_weights* grads, const float* d_out, int B, int T,
                      void* stream);
+/* The same backward pass in stages, so that the caller can start the gradient all-reduce of a stage (DDP buckets,
+ * train_ddp_v3mod2.py:822) while the next stage runs.  Order: begin, block depth-1, ..., block 0, end.
+ *   begin: final_layer.{0,1} gradients;   block i: every parameter of blocks.i (incl. its adaLN_modulation);
+ *   end:   patch_embed.* and t_embedder.* gradients. */
+int jat_dit_backward_begin(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
+                           const jat_dit_bwd_scratch* scratch, const jat_dit_weights* grads, const float* d_out, int B, int T,
+                           void* stream);
+int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
+                           const jat_dit_bwd_scratch* scratch, const jat_dit_weights* grads, int block, int B, int T,
+                           void* stream);
+int jat_dit_backward_end(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* saved,
+                         const jat_dit_bwd_scratch* scratch, const jat_dit_weights* grads, int B, int T, void* stream);
 
 /* Single-source patchify + cast (the transpose of the un-patchify epilogue, used on d_out):
  * out bf16 [B*N, C*P], out[b*N + n, c*P + p] = x[b, c, n*P + p] (0 past T). */
@@ -299,14 +313,16 @@ int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* tota
  * jat_adaln_bwd: backward of jat_adaln_norm_modulate.  dh bf16 [M, D] (M = B * tokens_per_batch), x the saved f32 input;
  *   dx (+)= d norm/dx (accumulate != 0 adds to the residual-stream gradient already in dx);
  *   dshift[b,:] += sum_n dh, dscale[b,:] += sum_n dh * norm(x)[*w]   (rows b * dmod_batch_stride; skipped if scale == NULL);
- *   dweight[D] += RMSNorm weight gradient (RMSNorm only, may be NULL).
+ *   dweight[D] += RMSNorm weight gradient (RMSNorm only, may be NULL).  rowstats_scratch: f32 [M, 2] (row mean / rstd
+ *   handed from the row-wise dx kernel to the column-sum kernel; may be NULL when scale == dweight == NULL).
  * jat_gate_bwd: backward of x += gate_b * y:  dy bf16 = gate_b * dx;  dgate[b,:] += sum_n dx * y;
  *   if dbias != NULL: dbias[:] += sum_b gate_b * sum_n dx (uses dxsum_scratch f32 [B, D]).
  * jat_colsum_bf16: out[c] += sum_m a[m, c] (bias gradients).    jat_cast_f32_bf16: elementwise cast.
  * -------------------------------------------------------------------------------------------- */
 int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* scale, int64_t mod_batch_stride,
                   const float* weight, int norm_kind, float eps, float* dx, int accumulate, float* dshift, float* dscale,
-                  int64_t dmod_batch_stride, float* dweight, int B, int tokens_per_batch, int D, void* stream);
+                  int64_t dmod_batch_stride, float* dweight, float* rowstats_scratch, int B, int tokens_per_batch, int D,
+                  void* stream);
 int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
                  void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
                  int tokens_per_batch, int D, void* stream);

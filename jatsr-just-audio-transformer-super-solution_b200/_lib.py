@@ -97,7 +97,7 @@ class DitSaved(C.Structure):
 
 class DitBwdScratch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dx", "dy", "dh", "da", "du", "dqkv", "dsum", "dq_acc", "dmod", "dmod_bf16",
-                                          "dxsum", "dout_p", "dpe", "dt_a", "dt_b")]
+                                          "dxsum", "dout_p", "dpe", "dt_a", "dt_b", "dt_acc", "rowstats")]
 
 
 # name -> (restype, argtypes); every symbol include/jat_b200.h declares
@@ -120,7 +120,7 @@ SIGNATURES = {
     "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_gqa_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_cfg_euler_update": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
-    "jat_adaln_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _i, _vp]),
+    "jat_adaln_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "jat_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "jat_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "jat_cast_f32_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
@@ -131,6 +131,12 @@ SIGNATURES = {
                                     _vp, _i, _i, _vp]),
     "jat_dit_backward": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved),
                                C.POINTER(DitBwdScratch), C.POINTER(DitWeights), _vp, _i, _i, _vp]),
+    "jat_dit_backward_begin": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved),
+                                     C.POINTER(DitBwdScratch), C.POINTER(DitWeights), _vp, _i, _i, _vp]),
+    "jat_dit_backward_block": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved),
+                                     C.POINTER(DitBwdScratch), C.POINTER(DitWeights), _i, _i, _i, _vp]),
+    "jat_dit_backward_end": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), C.POINTER(DitSaved),
+                                   C.POINTER(DitBwdScratch), C.POINTER(DitWeights), _i, _i, _vp]),
     "jat_dit_modulation": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp]),
     "jat_dit_forward_tokens": (_i, [_vp, C.POINTER(DitWeights), C.POINTER(DitWorkspace), _vp, _i, _vp, _i, _vp,
                                      _i64, _vp, _i, _i, _vp]),
@@ -193,7 +199,7 @@ def profile_begin(device_index: int) -> None:
 
 def profile_end(device_index: int) -> dict:
     """{kernel class: (total_ms, launches)} since profile_begin (synchronises the device)."""
-    n = 16
+    n = 32
     names = (C.c_char_p * n)()
     ms = (C.c_double * n)()
     cnt = (C.c_int64 * n)()

@@ -461,39 +461,46 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
 template <int NORM>
 static int launch_adaln_bwd(jat_ctx* ctx, const __nv_bfloat16* dh, const float* x, const float* scale, long long bstride,
                             const float* weight, float eps, float* dx, int accumulate, float* dshift, float* dscale,
-                            long long dbstride, float* dweight, int B, int ntok, int D, cudaStream_t s) {
+                            long long dbstride, float* dweight, float2* rowstats, int B, int ntok, int D, cudaStream_t s) {
+    const int M = B * ntok;
     const int nv = (D / 4 + 31) / 32;
-    dim3 grid((ntok + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block(BWD_WARPS * 32);
-    const size_t smem = (size_t)D * sizeof(float);
+    dim3 grid((M + BWD_WARPS - 1) / BWD_WARPS), block(BWD_WARPS * 32);
     pre_launch(ctx, TAG_ADALN_BWD, s);
-#define JAT_CASE(NV)                                                                                                  \
-    adaln_bwd_kernel<NV, NORM><<<grid, block, smem, s>>>(dh, x, scale, bstride, weight, eps, dx, accumulate, dshift, dscale, \
-                                                         dbstride, dweight, D, ntok)
+#define JAT_CASE(NV) \
+    adaln_bwd_dx_kernel<NV, NORM><<<grid, block, 0, s>>>(dh, x, scale, bstride, weight, eps, dx, accumulate, rowstats, M, D, ntok)
     if (nv <= 4) JAT_CASE(4);
     else if (nv <= 8) JAT_CASE(8);
     else if (nv <= 10) JAT_CASE(10);
     else JAT_CASE(16);
 #undef JAT_CASE
-    return post_launch(ctx, "adaln_bwd");
+    JAT_TRY(post_launch(ctx, "adaln_bwd_dx"));
+    if (scale == nullptr && dweight == nullptr) return 0;
+    dim3 grid2((ntok + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block2((D / 4 + 31) / 32 * 32);
+    pre_launch(ctx, TAG_ADALN_BWD, s);
+    adaln_bwd_colsum_kernel<NORM><<<grid2, block2, 0, s>>>(dh, x, rowstats, scale, bstride, weight, dshift, dscale, dbstride,
+                                                           dweight, D, ntok);
+    return post_launch(ctx, "adaln_bwd_colsum");
 }
 
 extern "C" int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* scale, int64_t mod_batch_stride,
                              const float* weight, int norm_kind, float eps, float* dx, int accumulate, float* dshift,
-                             float* dscale, int64_t dmod_batch_stride, float* dweight, int B, int tokens_per_batch, int D,
-                             void* stream) {
+                             float* dscale, int64_t dmod_batch_stride, float* dweight, float* rowstats_scratch, int B,
+                             int tokens_per_batch, int D, void* stream) {
     if (!ctx || !dh_bf16 || !x || !dx) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: null argument");
     if (scale != nullptr && (!dshift || !dscale)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: dshift/dscale missing");
+    if ((scale != nullptr || dweight != nullptr) && !rowstats_scratch)
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: rowstats_scratch (f32 [M, 2]) missing");
     if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
         return fail(JAT_ERR_BAD_SHAPE, "jat_adaln_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
     if (mod_batch_stride % 4 != 0 || dmod_batch_stride % 4 != 0) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: strides %% 4 != 0");
     cudaStream_t s = (cudaStream_t)stream;
     if (norm_kind == JAT_NORM_LAYERNORM)
         return launch_adaln_bwd<0>(ctx, (const __nv_bfloat16*)dh_bf16, x, scale, mod_batch_stride, nullptr, eps, dx, accumulate,
-                                   dshift, dscale, dmod_batch_stride, nullptr, B, tokens_per_batch, D, s);
+                                   dshift, dscale, dmod_batch_stride, nullptr, (float2*)rowstats_scratch, B, tokens_per_batch, D, s);
     if (norm_kind == JAT_NORM_RMSNORM) {
         if (!weight) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: RMSNorm needs a weight");
         return launch_adaln_bwd<1>(ctx, (const __nv_bfloat16*)dh_bf16, x, scale, mod_batch_stride, weight, eps, dx, accumulate,
-                                   dshift, dscale, dmod_batch_stride, dweight, B, tokens_per_batch, D, s);
+                                   dshift, dscale, dmod_batch_stride, dweight, (float2*)rowstats_scratch, B, tokens_per_batch, D, s);
     }
     return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: unknown norm_kind %d", norm_kind);
 }
@@ -508,18 +515,10 @@ extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, c
     cudaStream_t s = (cudaStream_t)stream;
     float* xs = dbias ? dxsum_scratch : nullptr;
     if (xs) JAT_CUDA(cudaMemsetAsync(xs, 0, (size_t)B * D * sizeof(float), s));
-    const int nv = (D / 4 + 31) / 32;
-    dim3 grid((tokens_per_batch + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block(BWD_WARPS * 32);
-    const size_t smem = (size_t)D * sizeof(float);
+    dim3 grid((tokens_per_batch + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block((D / 4 + 31) / 32 * 32);
     pre_launch(ctx, TAG_GATE_BWD, s);
-#define JAT_CASE(NV)                                                                                                     \
-    gate_bwd_kernel<NV><<<grid, block, smem, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride,                \
-                                                  (__nv_bfloat16*)dy_bf16, dgate, dmod_batch_stride, xs, D, tokens_per_batch)
-    if (nv <= 4) JAT_CASE(4);
-    else if (nv <= 8) JAT_CASE(8);
-    else if (nv <= 10) JAT_CASE(10);
-    else JAT_CASE(16);
-#undef JAT_CASE
+    gate_bwd_kernel<<<grid, block, 0, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride, (__nv_bfloat16*)dy_bf16,
+                                           dgate, dmod_batch_stride, xs, D, tokens_per_batch);
     JAT_TRY(post_launch(ctx, "gate_bwd"));
     if (dbias) {
         pre_launch(ctx, TAG_GATE_BWD, s);
@@ -531,11 +530,12 @@ extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, c
 
 extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream) {
     if (!ctx || !a_bf16 || !out) return fail(JAT_ERR_BAD_ARG, "jat_colsum_bf16: null argument");
-    if (M <= 0 || cols <= 0 || cols % 2 != 0 || lda % 2 != 0) return fail(JAT_ERR_BAD_SHAPE, "jat_colsum_bf16: need even cols / lda");
-    int chunks = (M + 63) / 64;
-    const int cap = (ctx->sm_count * 16) / ((cols + 255) / 256) + 1;
+    if (M <= 0 || cols <= 0 || cols % 4 != 0 || lda % 4 != 0 || (reinterpret_cast<uintptr_t>(a_bf16) & 7) != 0)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_colsum_bf16: need cols %% 4 == 0, lda %% 4 == 0, 8-byte aligned input");
+    int chunks = (M + 31) / 32;
+    const int cap = (ctx->sm_count * 16) / ((cols + 511) / 512) + 1;
     if (chunks > cap) chunks = cap;
-    dim3 grid((cols + 255) / 256, chunks);
+    dim3 grid((cols + 511) / 512, chunks);
     pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
     colsum_bf16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, (long long)lda, M, cols, out);
     return post_launch(ctx, "colsum_bf16");
@@ -852,9 +852,9 @@ static int wgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* X, int
     e.a_transposed = 1; e.w_transposed = 1;
     const int bn = (Kin % 256 == 0) ? 256 : 128;
     const long long tiles = (long long)((Nout + 255) / 256) * (Kin / bn);
-    long long want = (4LL * (ctx->sm_count / 2) + tiles - 1) / tiles;
+    long long want = (2LL * (ctx->sm_count / 2) + tiles - 1) / tiles;
     const int kblocks = (Mtok + GEMM_BK - 1) / GEMM_BK;
-    if (want > 16) want = 16;
+    if (want > 8) want = 8;
     if (want > kblocks) want = kblocks;
     e.k_splits = (int)(want < 1 ? 1 : want);
     return jat_gemm_bf16(ctx, dY, ld_dy, X, ld_x, Nout, Kin, Mtok, &e, -1, 0, stream);
@@ -867,77 +867,124 @@ static int dgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* W, int
     return jat_gemm_bf16(ctx, dY, ld_dy, W, Kin, Mtok, Kin, Nout, &e, -1, 0, stream);
 }
 
-extern "C" int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* sv,
-                                const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, const float* d_out, int B, int T,
-                                void* stream) {
-    if (!ctx || !w || !ws || !sv || !sc || !gr || !d_out) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward: null argument");
-    const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
-    const int N = (T + P - 1) / P, M = B * N, Hq = w->n_q_heads, Hkv = w->n_kv_heads;
-    const int QKV = (Hq + 2 * Hkv) * 64, KIN = 2 * C * P, NM = w->depth * 6 * D, CP = C * P;
-    const int64_t MD = (int64_t)M * D;
+// The backward pass in three stages, so that a framework can hand the gradients of a stage to its gradient
+// all-reduce (DDP buckets) while the next stage runs:  begin (final layer) -> block depth-1 ... block 0 -> end
+// (patch embed + timestep path).  dmod is block-major: [depth][B][6*hidden].
+struct BwdDims {
+    int D, P, C, F, BD, N, M, Hq, Hkv, QKV, KIN, SIXD, CP;
+    int64_t MD;
+};
+static BwdDims bwd_dims(const jat_dit_weights* w, int B, int T) {
+    BwdDims d;
+    d.D = w->hidden; d.P = w->patch_len; d.C = w->channels; d.F = w->mlp_hidden; d.BD = w->bottleneck;
+    d.N = (T + d.P - 1) / d.P; d.M = B * d.N; d.Hq = w->n_q_heads; d.Hkv = w->n_kv_heads;
+    d.QKV = (d.Hq + 2 * d.Hkv) * 64; d.KIN = 2 * d.C * d.P; d.SIXD = 6 * d.D; d.CP = d.C * d.P;
+    d.MD = (int64_t)d.M * d.D;
+    return d;
+}
+
+extern "C" int jat_dit_backward_begin(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
+                                      const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr,
+                                      const float* d_out, int B, int T, void* stream) {
+    if (!ctx || !w || !ws || !sv || !sc || !gr || !d_out) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_begin: null argument");
+    const BwdDims d = bwd_dims(w, B, T);
     cudaStream_t s = (cudaStream_t)stream;
     const bool rms = w->norm_kind == JAT_NORM_RMSNORM;
-    JAT_CUDA(cudaMemsetAsync(sc->dmod, 0, (size_t)B * NM * sizeof(float), s));
+    JAT_CUDA(cudaMemsetAsync(sc->dmod, 0, (size_t)w->depth * B * d.SIXD * sizeof(float), s));
+    JAT_CUDA(cudaMemsetAsync(sc->dt_acc, 0, (size_t)B * d.D * sizeof(float), s));
+    // final layer: out = unpatchify(hf Wf^T + bf), hf = norm(x_L)
+    JAT_TRY(jat_patchify_single(ctx, d_out, sc->dout_p, B, d.C, T, d.P, stream));
+    JAT_TRY(wgrad(ctx, sc->dout_p, d.CP, ws->h, d.D, (float*)gr->final_w, d.CP, d.D, d.M, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->dout_p, d.CP, d.M, d.CP, (float*)gr->final_b, stream));
+    JAT_TRY(dgrad(ctx, sc->dout_p, d.CP, w->final_w, d.D, d.CP, d.M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    return jat_adaln_bwd(ctx, sc->dh, ws->x, nullptr, 0, w->final_norm_w, w->norm_kind, w->norm_eps, sc->dx, 0, nullptr,
+                         nullptr, 0, rms ? (float*)gr->final_norm_w : nullptr, sc->rowstats, B, d.N, d.D, stream);
+}
 
-    // ---- final layer: out = unpatchify(hf Wf^T + bf), hf = norm(x_L)
-    JAT_TRY(jat_patchify_single(ctx, d_out, sc->dout_p, B, C, T, P, stream));
-    JAT_TRY(wgrad(ctx, sc->dout_p, CP, ws->h, D, (float*)gr->final_w, CP, D, M, stream));
-    JAT_TRY(jat_colsum_bf16(ctx, sc->dout_p, CP, M, CP, (float*)gr->final_b, stream));
-    JAT_TRY(dgrad(ctx, sc->dout_p, CP, w->final_w, D, CP, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
-    JAT_TRY(jat_adaln_bwd(ctx, sc->dh, ws->x, nullptr, 0, w->final_norm_w, w->norm_kind, w->norm_eps, sc->dx, 0, nullptr,
-                          nullptr, 0, rms ? (float*)gr->final_norm_w : nullptr, B, N, D, stream));
-
-    for (int i = w->depth - 1; i >= 0; --i) {
-        const float* m = ws->mod + (int64_t)i * 6 * D;
-        float* dm = sc->dmod + (int64_t)i * 6 * D;
-        const void* h1 = at(sv->h1, i, MD, 2);
-        const void* qkv = at(sv->qkv, i, (int64_t)M * QKV, 2);
-        const void* attn = at(sv->attn, i, MD, 2);
-        const void* h2 = at(sv->h2, i, MD, 2);
-        const void* u = at(sv->u, i, (int64_t)M * F, 2);
-        const void* mact = at(sv->mact, i, (int64_t)M * F, 2);
-        // ---- MLP branch: x2 = x1 + gate_mlp * (gelu(h2 W1^T + b1) W2^T + b2)
-        JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, NM, sc->dxsum,
-                             (float*)gr->b2[i], B, N, D, stream));
-        JAT_TRY(wgrad(ctx, sc->dy, D, mact, F, (float*)gr->w2[i], D, F, M, stream));
-        JAT_TRY(dgrad(ctx, sc->dy, D, w->w2[i], F, D, M, sc->du, JAT_ACT_GELU_ERF, u, stream));
-        JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
-        JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
-        JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
-        JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), m + 4 * D, NM,
-                              w->norm2_w ? w->norm2_w[i] : nullptr, w->norm_kind, w->norm_eps, sc->dx, 1, dm + 3 * D, dm + 4 * D,
-                              NM, rms ? (float*)gr->norm2_w[i] : nullptr, B, N, D, stream));
-        // ---- attention branch: x1 = x + gate_msa * (attn(h1) Wo^T)
-        JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, NM, nullptr, nullptr, B, N, D,
-                             stream));
-        JAT_TRY(wgrad(ctx, sc->dy, D, attn, D, (float*)gr->wo[i], D, D, M, stream));
-        JAT_TRY(dgrad(ctx, sc->dy, D, w->wo[i], D, D, M, sc->da, JAT_ACT_NONE, nullptr, stream));
-        JAT_TRY(jat_gqa_attention_bwd(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), sc->dsum,
-                                      sc->dq_acc, sc->dqkv, w->rope_cos, w->rope_sin, B, N, Hq, Hkv, 64, stream));
-        JAT_TRY(wgrad(ctx, sc->dqkv, QKV, h1, D, (float*)gr->wqkv[i], QKV, D, M, stream));
-        JAT_TRY(dgrad(ctx, sc->dqkv, QKV, w->wqkv[i], D, QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
-        JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,
-                              w->norm_kind, w->norm_eps, sc->dx, 1, dm, dm + D, NM, rms ? (float*)gr->norm1_w[i] : nullptr, B, N, D,
-                              stream));
+extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
+                                      const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr,
+                                      int i, int B, int T, void* stream) {
+    if (!ctx || !w || !ws || !sv || !sc || !gr) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_block: null argument");
+    if (i < 0 || i >= w->depth) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_block: block index %d out of range", i);
+    const BwdDims d = bwd_dims(w, B, T);
+    const int D = d.D, F = d.F, M = d.M, N = d.N, NM = w->depth * d.SIXD;
+    const int64_t MD = d.MD;
+    const bool rms = w->norm_kind == JAT_NORM_RMSNORM;
+    const float* m = ws->mod + (int64_t)i * d.SIXD;               // forward modulation: [B][depth*6D], row stride NM
+    float* dm = sc->dmod + (int64_t)i * B * d.SIXD;               // its gradient: block-major, row stride 6D
+    const void* h1 = at(sv->h1, i, MD, 2);
+    const void* qkv = at(sv->qkv, i, (int64_t)M * d.QKV, 2);
+    const void* attn = at(sv->attn, i, MD, 2);
+    const void* h2 = at(sv->h2, i, MD, 2);
+    const void* u = at(sv->u, i, (int64_t)M * F, 2);
+    const void* mact = at(sv->mact, i, (int64_t)M * F, 2);
+    // ---- MLP branch: x2 = x1 + gate_mlp * (gelu(h2 W1^T + b1) W2^T + b2)
+    JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, d.SIXD, sc->dxsum,
+                         (float*)gr->b2[i], B, N, D, stream));
+    JAT_TRY(wgrad(ctx, sc->dy, D, mact, F, (float*)gr->w2[i], D, F, M, stream));
+    JAT_TRY(dgrad(ctx, sc->dy, D, w->w2[i], F, D, M, sc->du, JAT_ACT_GELU_ERF, u, stream));
+    JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
+    JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
+                          w->norm_kind, w->norm_eps, sc->dx, 1, dm + 3 * D, dm + 4 * D, d.SIXD,
+                          rms ? (float*)gr->norm2_w[i] : nullptr, sc->rowstats, B, N, D, stream));
+    // ---- attention branch: x1 = x + gate_msa * (attn(h1) Wo^T)
+    JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, d.SIXD, nullptr, nullptr, B, N, D,
+                         stream));
+    JAT_TRY(wgrad(ctx, sc->dy, D, attn, D, (float*)gr->wo[i], D, D, M, stream));
+    JAT_TRY(dgrad(ctx, sc->dy, D, w->wo[i], D, D, M, sc->da, JAT_ACT_NONE, nullptr, stream));
+    JAT_TRY(jat_gqa_attention_bwd(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * d.Hq * N, 4), sc->dsum,
+                                  sc->dq_acc, sc->dqkv, w->rope_cos, w->rope_sin, B, N, d.Hq, d.Hkv, 64, stream));
+    JAT_TRY(wgrad(ctx, sc->dqkv, d.QKV, h1, D, (float*)gr->wqkv[i], d.QKV, D, M, stream));
+    JAT_TRY(dgrad(ctx, sc->dqkv, d.QKV, w->wqkv[i], D, d.QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,
+                          w->norm_kind, w->norm_eps, sc->dx, 1, dm, dm + D, d.SIXD, rms ? (float*)gr->norm1_w[i] : nullptr,
+                          sc->rowstats, B, N, D, stream));
+    // ---- this block's adaLN_modulation Linear: mod_i = t_act Wada_i^T + bada_i  (dmod_i is complete now)
+    void* dmb = at(sc->dmod_bf16, i, (int64_t)B * d.SIXD, 2);
+    JAT_TRY(jat_cast_f32_bf16(ctx, dm, dmb, (int64_t)B * d.SIXD, stream));
+    float* g_ada_w = (float*)gr->ada_w + (int64_t)i * d.SIXD * D;
+    const char* ada_w = (const char*)w->ada_w + (int64_t)i * d.SIXD * D * 2;
+    JAT_TRY(wgrad(ctx, dmb, d.SIXD, ws->t_act, D, g_ada_w, d.SIXD, D, B, stream));
+    JAT_TRY(jat_colsum_bf16(ctx, dmb, d.SIXD, B, d.SIXD, (float*)gr->ada_b + (int64_t)i * d.SIXD, stream));
+    {   // d t_act (f32, summed over blocks) += dmod_i Wada_i
+        jat_gemm_epilogue e = epi_plain(JAT_EPI_ACCUM, sc->dt_acc, D);
+        e.w_transposed = 1; e.k_splits = 16;
+        JAT_TRY(jat_gemm_bf16(ctx, dmb, d.SIXD, ada_w, D, B, D, d.SIXD, &e, -1, 0, stream));
     }
+    return 0;
+}
 
+extern "C" int jat_dit_backward_end(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
+                                    const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, int B,
+                                    int T, void* stream) {
+    if (!ctx || !w || !ws || !sv || !sc || !gr) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_end: null argument");
+    const BwdDims d = bwd_dims(w, B, T);
+    const int D = d.D, BD = d.BD, M = d.M;
     // ---- patch embed: x0 = gelu(patches W1^T + b1) W2^T + b2   (no gradient flows to the inputs)
-    JAT_TRY(jat_cast_f32_bf16(ctx, sc->dx, sc->dy, MD, stream));
+    JAT_TRY(jat_cast_f32_bf16(ctx, sc->dx, sc->dy, d.MD, stream));
     JAT_TRY(wgrad(ctx, sc->dy, D, ws->pe_hid, BD, (float*)gr->pe_w2, D, BD, M, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->dy, D, M, D, (float*)gr->pe_b2, stream));
     JAT_TRY(dgrad(ctx, sc->dy, D, w->pe_w2, BD, D, M, sc->dpe, JAT_ACT_GELU_ERF, sv->pe_u, stream));
-    JAT_TRY(wgrad(ctx, sc->dpe, BD, ws->patches, KIN, (float*)gr->pe_w1, BD, KIN, M, stream));
+    JAT_TRY(wgrad(ctx, sc->dpe, BD, ws->patches, d.KIN, (float*)gr->pe_w1, BD, d.KIN, M, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->dpe, BD, M, BD, (float*)gr->pe_b1, stream));
-
-    // ---- timestep path: mod = silu(t_emb) Wada^T + bada,  t_emb = silu(feat W1^T + b1) W2^T + b2
-    JAT_TRY(jat_cast_f32_bf16(ctx, sc->dmod, sc->dmod_bf16, (int64_t)B * NM, stream));
-    JAT_TRY(wgrad(ctx, sc->dmod_bf16, NM, ws->t_act, D, (float*)gr->ada_w, NM, D, B, stream));
-    JAT_TRY(jat_colsum_bf16(ctx, sc->dmod_bf16, NM, B, NM, (float*)gr->ada_b, stream));
-    JAT_TRY(dgrad(ctx, sc->dmod_bf16, NM, w->ada_w, D, NM, B, sc->dt_a, JAT_ACT_SILU, sv->t_u2, stream));  // d t_emb (pre-SiLU)
+    // ---- timestep path: t_act = silu(t_emb), t_emb = silu(feat W1^T + b1) W2^T + b2
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    dact_mul_kernel<ACT_SILU><<<(B * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sc->dt_acc, (const __nv_bfloat16*)sv->t_u2,
+                                                                                   (__nv_bfloat16*)sc->dt_a, (long long)B * D);
+    JAT_TRY(post_launch(ctx, "dact_mul"));
     JAT_TRY(wgrad(ctx, sc->dt_a, D, ws->t_hid, D, (float*)gr->te_w2, D, D, B, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->dt_a, D, B, D, (float*)gr->te_b2, stream));
     JAT_TRY(dgrad(ctx, sc->dt_a, D, w->te_w2, D, D, B, sc->dt_b, JAT_ACT_SILU, sv->t_u1, stream));
     JAT_TRY(wgrad(ctx, sc->dt_b, D, ws->t_feat, D, (float*)gr->te_w1, D, D, B, stream));
-    JAT_TRY(jat_colsum_bf16(ctx, sc->dt_b, D, B, D, (float*)gr->te_b1, stream));
-    return 0;
+    return jat_colsum_bf16(ctx, sc->dt_b, D, B, D, (float*)gr->te_b1, stream);
+}
+
+extern "C" int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* sv,
+                                const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, const float* d_out, int B, int T,
+                                void* stream) {
+    JAT_TRY(jat_dit_backward_begin(ctx, w, ws, sv, sc, gr, d_out, B, T, stream));
+    for (int i = w->depth - 1; i >= 0; --i) JAT_TRY(jat_dit_backward_block(ctx, w, ws, sv, sc, gr, i, B, T, stream));
+    return jat_dit_backward_end(ctx, w, ws, sv, sc, gr, B, T, stream);
 }

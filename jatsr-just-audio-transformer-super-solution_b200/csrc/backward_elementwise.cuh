@@ -1,8 +1,8 @@
 // HBM-bound kernels of the DiT block BACKWARD pass (training step, train_ddp_v3mod2.py:886-922 runs autograd
-// through jat_audiosr_v2.py:265-289).  All single-pass, vectorised; per-batch-item column reductions (the gradients
-// of the adaLN shift / scale / gate vectors, which are broadcast over the N tokens of a batch item) are
-// accumulated in registers over the rows a CTA owns, reduced across its warps in shared memory and flushed with
-// one f32 atomicAdd per column per CTA.
+// through jat_audiosr_v2.py:265-289).  All single-pass, vectorised.  Thread = 4 fixed columns and a CTA walks over
+// token rows of ONE batch item, so the per-batch-item column reductions (the gradients of the adaLN shift / scale /
+// gate vectors, which are broadcast over the N tokens of a batch item) accumulate in a few registers and are
+// flushed with one f32 atomicAdd per column per CTA.
 #pragma once
 #include "common.cuh"
 
@@ -16,32 +16,6 @@ __device__ __forceinline__ float4 bf16x4_to_f32(uint2 v) {
                        __uint_as_float(v.y & 0xffff0000u));
 }
 
-// cross-warp reduction of per-lane column partials acc[NV] (float4 each; lane owns vec4 columns lane + 32 i) and
-// atomicAdd into dst[0 .. D)
-template <int NV>
-__device__ __forceinline__ void cta_colsum_flush(const float4 (&acc)[NV], float* smem /* [D] */, float* dst, int nvec) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* s4 = reinterpret_cast<float4*>(smem);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    for (int w = 0; w < BWD_WARPS; ++w) {  // warps take turns: no shared-memory atomics needed
-        if (warp == w) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int idx = lane + 32 * i;
-                if (idx < nvec) {
-                    float4 t = s4[idx];
-                    t.x += acc[i].x; t.y += acc[i].y; t.z += acc[i].z; t.w += acc[i].w;
-                    s4[idx] = t;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < nvec * 4; i += blockDim.x) atomicAdd(dst + i, smem[i]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // AdaLN backward.  Forward (jat_audiosr_v2.py:278-279 / jat_audiosr_v3.py RMSNorm):
 //     y = norm(x) [* w]          h = y * (1 + scale_b) + shift_b
@@ -49,119 +23,143 @@ __device__ __forceinline__ void cta_colsum_flush(const float4 (&acc)[NV], float*
 //     dshift_b += sum_n dh        dscale_b += sum_n dh * y        [dw += sum_rows dh (1+scale) * xhat   (RMSNorm)]
 //     LayerNorm: g = dh (1+scale);            dx (+)= rstd (g - mean(g) - xhat mean(g xhat))
 //     RMSNorm:   g = dh (1+scale) w;          dx (+)= rstd (g - xhat mean(g xhat)),   xhat = x rstd
-// grid = (ceil(N / 32), B): a CTA owns 32 consecutive tokens of one batch item.  dx is accumulated in place
-// (accumulate = 1: the residual-stream gradient already holds the skip-path gradient) or overwritten.
+// Two kernels, each with the thread mapping its reductions want:
+//   adaln_bwd_dx_kernel      one WARP per token row (row statistics are warp-shuffle reductions, like the forward
+//                            kernel); writes dx and the row's (mean, rstd);
+//   adaln_bwd_colsum_kernel  one THREAD per 4 columns, a CTA walks 32 rows of one batch item (column sums in
+//                            registers, coalesced 5 KB row reads, one atomicAdd per column per CTA).
+// dx is accumulated in place (accumulate = 1: the residual-stream gradient already holds the skip-path gradient) or
+// overwritten.
 // ------------------------------------------------------------------------------------------------
 template <int NV, int NORM_KIND>
 __global__ void __launch_bounds__(BWD_WARPS * 32)
-adaln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale,
-                 long long mod_bstride, const float* __restrict__ weight, float eps, float* __restrict__ dx, int accumulate,
-                 float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_bstride, float* __restrict__ dweight,
-                 int D, int tokens_per_batch) {
-    extern __shared__ float red_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y;
+adaln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale,
+                    long long mod_bstride, const float* __restrict__ weight, float eps, float* __restrict__ dx, int accumulate,
+                    float2* __restrict__ rowstats, int M, int D, int tokens_per_batch) {
+    const int row = blockIdx.x * BWD_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    const bool has_mod = scale != nullptr;
-    const float4* sc = has_mod ? reinterpret_cast<const float4*>(scale + (long long)b * mod_bstride) : nullptr;
-    const float4* wv = reinterpret_cast<const float4*>(weight);
     const float inv_d = 1.0f / (float)D;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    const uint2* gr = reinterpret_cast<const uint2*>(dh + (long long)row * D);
+    float4 xv[NV], gv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        xv[i] = idx < nvec ? __ldcs(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gv[i] = idx < nvec ? bf16x4_to_f32(__ldcs(gr + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mean = 0.f, rstd;
+    if constexpr (NORM_KIND == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        mean = warp_sum(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < nvec) {
+                const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+                q += (a * a + bb * bb) + (c * c + d * d);
+            }
+        }
+        rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    } else {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+        rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    }
+    if (lane == 0 && rowstats != nullptr) rowstats[row] = make_float2(mean, rstd);
+    const bool has_mod = scale != nullptr;
+    const float4* sc = has_mod ? reinterpret_cast<const float4*>(scale + (long long)(row / tokens_per_batch) * mod_bstride) : nullptr;
+    const float4* wv = reinterpret_cast<const float4*>(weight);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            const float4 xh = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd,
+                                          (xv[i].w - mean) * rstd);
+            float4 g = gv[i];
+            if (has_mod) {
+                const float4 s4 = __ldg(sc + idx);
+                g.x *= 1.0f + s4.x; g.y *= 1.0f + s4.y; g.z *= 1.0f + s4.z; g.w *= 1.0f + s4.w;
+            }
+            if constexpr (NORM_KIND == 1) {
+                const float4 w4 = __ldg(wv + idx);
+                g.x *= w4.x; g.y *= w4.y; g.z *= w4.z; g.w *= w4.w;
+            }
+            sg += (g.x + g.y) + (g.z + g.w);
+            sgx += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+            xv[i] = xh;
+            gv[i] = g;
+        }
+    }
+    const float mg = NORM_KIND == 0 ? warp_sum(sg) * inv_d : 0.0f;
+    const float mgx = warp_sum(sgx) * inv_d;
+    float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            float4 o;
+            o.x = rstd * (gv[i].x - mg - xv[i].x * mgx);
+            o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
+            o.z = rstd * (gv[i].z - mg - xv[i].z * mgx);
+            o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
+            if (accumulate) {
+                const float4 old = dxr[idx];
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            dxr[idx] = o;
+        }
+    }
+}
 
-    float4 a_shift[NV], a_scale[NV], a_w[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) a_shift[i] = a_scale[i] = a_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int rr = warp; rr < BWD_ROWS_PER_CTA; rr += BWD_WARPS) {
-        const int n = blockIdx.x * BWD_ROWS_PER_CTA + rr;
-        if (n >= tokens_per_batch) break;
-        const long long row = (long long)b * tokens_per_batch + n;
-        const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-        const uint2* gr = reinterpret_cast<const uint2*>(dh + row * D);
-        float4 xv[NV], gv[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int idx = lane + 32 * i;
-            xv[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-            gv[i] = idx < nvec ? bf16x4_to_f32(__ldg(gr + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float mean = 0.f, rstd;
-        if constexpr (NORM_KIND == 0) {
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
-            mean = warp_sum(s) * inv_d;
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                if (lane + 32 * i < nvec) {
-                    const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
-                    q += (a * a + bb * bb) + (c * c + d * d);
-                }
-            }
-            rstd = rsqrtf(warp_sum(q) * inv_d + eps);
-        } else {
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
-            rstd = rsqrtf(warp_sum(q) * inv_d + eps);
-        }
-        // xhat in xv, g (gradient w.r.t. xhat) in gv; column partials on the way
-        float sg = 0.f, sgx = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                float4 xh = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd,
-                                        (xv[i].w - mean) * rstd);
-                float4 g = gv[i];
-                float4 y = xh;
-                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if constexpr (NORM_KIND == 1) {
-                    w4 = __ldg(wv + idx);
-                    y.x *= w4.x; y.y *= w4.y; y.z *= w4.z; y.w *= w4.w;
-                }
-                if (has_mod) {
-                    a_shift[i].x += g.x; a_shift[i].y += g.y; a_shift[i].z += g.z; a_shift[i].w += g.w;
-                    a_scale[i].x += g.x * y.x; a_scale[i].y += g.y * y.y; a_scale[i].z += g.z * y.z; a_scale[i].w += g.w * y.w;
-                    const float4 s4 = __ldg(sc + idx);
-                    g.x *= 1.0f + s4.x; g.y *= 1.0f + s4.y; g.z *= 1.0f + s4.z; g.w *= 1.0f + s4.w;
-                }
-                if constexpr (NORM_KIND == 1) {
-                    a_w[i].x += g.x * xh.x; a_w[i].y += g.y * xh.y; a_w[i].z += g.z * xh.z; a_w[i].w += g.w * xh.w;
-                    g.x *= w4.x; g.y *= w4.y; g.z *= w4.z; g.w *= w4.w;
-                }
-                sg += (g.x + g.y) + (g.z + g.w);
-                sgx += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
-                xv[i] = xh;
-                gv[i] = g;
-            }
-        }
-        const float mg = NORM_KIND == 0 ? warp_sum(sg) * inv_d : 0.0f;
-        const float mgx = warp_sum(sgx) * inv_d;
-        float4* dxr = reinterpret_cast<float4*>(dx + row * D);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                float4 o;
-                o.x = rstd * (gv[i].x - mg - xv[i].x * mgx);
-                o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
-                o.z = rstd * (gv[i].z - mg - xv[i].z * mgx);
-                o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
-                if (accumulate) {
-                    const float4 old = dxr[idx];
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                dxr[idx] = o;
-            }
+template <int NORM_KIND>
+__global__ void __launch_bounds__(512)
+adaln_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float2* __restrict__ rowstats,
+                        const float* __restrict__ scale, long long mod_bstride, const float* __restrict__ weight,
+                        float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_bstride,
+                        float* __restrict__ dweight, int D, int tokens_per_batch) {
+    const int c4 = threadIdx.x;
+    if (c4 >= (D >> 2)) return;
+    const int b = blockIdx.y;
+    const bool has_mod = scale != nullptr;
+    float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), w4 = sc4;
+    if (has_mod) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * mod_bstride) + c4);
+        sc4 = make_float4(1.0f + t.x, 1.0f + t.y, 1.0f + t.z, 1.0f + t.w);
+    }
+    if (NORM_KIND == 1) w4 = __ldg(reinterpret_cast<const float4*>(weight) + c4);
+    float4 a_shift = make_float4(0.f, 0.f, 0.f, 0.f), a_scale = a_shift, a_w = a_shift;
+    const int n0 = blockIdx.x * BWD_ROWS_PER_CTA;
+    const int n1 = min(n0 + BWD_ROWS_PER_CTA, tokens_per_batch);
+    const long long row0 = (long long)b * tokens_per_batch;
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n) {
+        const long long row = row0 + n;
+        const float2 st = __ldg(rowstats + row);
+        const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + row * D) + c4);
+        const float4 g = bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(dh + row * D) + c4));
+        const float4 xh = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
+        a_shift.x += g.x; a_shift.y += g.y; a_shift.z += g.z; a_shift.w += g.w;
+        a_scale.x += g.x * xh.x * w4.x; a_scale.y += g.y * xh.y * w4.y; a_scale.z += g.z * xh.z * w4.z; a_scale.w += g.w * xh.w * w4.w;
+        if (NORM_KIND == 1) {
+            a_w.x += g.x * sc4.x * xh.x; a_w.y += g.y * sc4.y * xh.y; a_w.z += g.z * sc4.z * xh.z; a_w.w += g.w * sc4.w * xh.w;
         }
     }
     if (has_mod) {
-        cta_colsum_flush<NV>(a_shift, red_smem, dshift + (long long)b * dmod_bstride, nvec);
-        cta_colsum_flush<NV>(a_scale, red_smem, dscale + (long long)b * dmod_bstride, nvec);
+        float* p1 = dshift + (long long)b * dmod_bstride + c4 * 4;
+        float* p2 = dscale + (long long)b * dmod_bstride + c4 * 4;
+        atomicAdd(p1, a_shift.x); atomicAdd(p1 + 1, a_shift.y); atomicAdd(p1 + 2, a_shift.z); atomicAdd(p1 + 3, a_shift.w);
+        atomicAdd(p2, a_scale.x); atomicAdd(p2 + 1, a_scale.y); atomicAdd(p2 + 2, a_scale.z); atomicAdd(p2 + 3, a_scale.w);
     }
-    if constexpr (NORM_KIND == 1) {
-        if (dweight != nullptr) cta_colsum_flush<NV>(a_w, red_smem, dweight, nvec);
+    if (NORM_KIND == 1 && dweight != nullptr) {
+        float* p3 = dweight + c4 * 4;
+        atomicAdd(p3, a_w.x); atomicAdd(p3 + 1, a_w.y); atomicAdd(p3 + 2, a_w.z); atomicAdd(p3 + 3, a_w.w);
     }
 }
 
@@ -169,42 +167,36 @@ adaln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__
 // Gate backward.  Forward (jat_audiosr_v2.py:281,287): x += gate_b * y.   Given the residual-stream gradient dx (f32)
 // and the saved y (bf16):   dy = gate_b * dx (bf16, the A operand of the following dgrad / wgrad GEMMs)
 //     dgate_b += sum_n dx * y          dxsum_b += sum_n dx   (db = sum_b gate_b * dxsum_b, finished by gate_bias_grad_kernel)
+// Thread = 4 fixed columns; a CTA (D/4 threads) walks over 32 token rows of one batch item, so every row access is one
+// fully coalesced 5 KB read and the column partials live in 8 registers -- no cross-thread reduction at all.
 // ------------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(BWD_WARPS * 32)
+__global__ void __launch_bounds__(512)
 gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
                 long long mod_bstride, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dmod_bstride,
                 float* __restrict__ dxsum, int D, int tokens_per_batch) {
-    extern __shared__ float red_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = threadIdx.x;  // vec4 column
+    if (c4 >= (D >> 2)) return;
     const int b = blockIdx.y;
-    const int nvec = D >> 2;
-    const float4* gt = reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride);
-    float4 a_gate[NV], a_sum[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) a_gate[i] = a_sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int rr = warp; rr < BWD_ROWS_PER_CTA; rr += BWD_WARPS) {
-        const int n = blockIdx.x * BWD_ROWS_PER_CTA + rr;
-        if (n >= tokens_per_batch) break;
-        const long long row = (long long)b * tokens_per_batch + n;
-        const float4* dr = reinterpret_cast<const float4*>(dx + row * D);
-        const uint2* yr = reinterpret_cast<const uint2*>(y + row * D);
-        uint2* or_ = reinterpret_cast<uint2*>(dy + row * D);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                const float4 d = dr[idx];
-                const float4 yv = bf16x4_to_f32(__ldg(yr + idx));
-                const float4 g4 = __ldg(gt + idx);
-                a_gate[i].x += d.x * yv.x; a_gate[i].y += d.y * yv.y; a_gate[i].z += d.z * yv.z; a_gate[i].w += d.w * yv.w;
-                a_sum[i].x += d.x; a_sum[i].y += d.y; a_sum[i].z += d.z; a_sum[i].w += d.w;
-                or_[idx] = make_uint2(pack_bf16(d.x * g4.x, d.y * g4.y), pack_bf16(d.z * g4.z, d.w * g4.w));
-            }
-        }
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride) + c4);
+    float4 a_gate = make_float4(0.f, 0.f, 0.f, 0.f), a_sum = a_gate;
+    const int n0 = blockIdx.x * BWD_ROWS_PER_CTA;
+    const int n1 = min(n0 + BWD_ROWS_PER_CTA, tokens_per_batch);
+    const long long row0 = (long long)b * tokens_per_batch;
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n) {
+        const long long off = (row0 + n) * D;
+        const float4 d = __ldcs(reinterpret_cast<const float4*>(dx + off) + c4);
+        const float4 yv = bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(y + off) + c4));
+        a_gate.x += d.x * yv.x; a_gate.y += d.y * yv.y; a_gate.z += d.z * yv.z; a_gate.w += d.w * yv.w;
+        a_sum.x += d.x; a_sum.y += d.y; a_sum.z += d.z; a_sum.w += d.w;
+        reinterpret_cast<uint2*>(dy + off)[c4] = make_uint2(pack_bf16(d.x * g4.x, d.y * g4.y), pack_bf16(d.z * g4.z, d.w * g4.w));
     }
-    cta_colsum_flush<NV>(a_gate, red_smem, dgate + (long long)b * dmod_bstride, nvec);
-    if (dxsum != nullptr) cta_colsum_flush<NV>(a_sum, red_smem, dxsum + (long long)b * D, nvec);
+    float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
+    atomicAdd(dg, a_gate.x); atomicAdd(dg + 1, a_gate.y); atomicAdd(dg + 2, a_gate.z); atomicAdd(dg + 3, a_gate.w);
+    if (dxsum != nullptr) {
+        float* ds = dxsum + (long long)b * D + c4 * 4;
+        atomicAdd(ds, a_sum.x); atomicAdd(ds + 1, a_sum.y); atomicAdd(ds + 2, a_sum.z); atomicAdd(ds + 3, a_sum.w);
+    }
 }
 
 // db[d] += sum_b gate[b, d] * dxsum[b, d]      (bias of mlp.3: y = acc + bias enters x through the gate)
@@ -219,20 +211,31 @@ __global__ void gate_bias_grad_kernel(const float* __restrict__ gate, long long 
 
 // ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix: out[c] += sum_m a[m, c]   (bias gradients of mlp.0, patch_embed, final_layer, ...).
-// grid = (ceil(cols / 256), row chunks); thread = 2 adjacent columns, rows strided by the chunk count.
+// grid = (ceil(cols / 512), row chunks); thread = 4 adjacent columns (8-byte loads), rows strided by the chunk count,
+// 8 loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, int M, int cols, float* __restrict__ out) {
-    const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+    const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
     if (c >= cols) return;
-    float s0 = 0.f, s1 = 0.f;
-    for (int m = blockIdx.y; m < M; m += gridDim.y) {
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(a + (long long)m * lda + c));
-        s0 += __uint_as_float(v << 16);
-        s1 += __uint_as_float(v & 0xffff0000u);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int step = gridDim.y;
+    int m = blockIdx.y;
+    for (; m + 7 * step < M; m += 8 * step) {
+        uint2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const uint2*>(a + (long long)(m + j * step) * lda + c));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 f = bf16x4_to_f32(v[j]);
+            s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;
+        }
     }
-    atomicAdd(out + c, s0);
-    if (c + 1 < cols) atomicAdd(out + c + 1, s1);
+    for (; m < M; m += step) {
+        const float4 f = bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(a + (long long)m * lda + c)));
+        s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;
+    }
+    atomicAdd(out + c, s.x); atomicAdd(out + c + 1, s.y); atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
 }
 
 // f32 -> bf16 cast of a matrix (gradients that become GEMM operands, e.g. dmod)
@@ -244,6 +247,21 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
     } else {
         for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
     }
+}
+
+// out (bf16) = g (f32) * act'(u)   (tiny: the activation backward of the timestep path)
+template <int ACT>
+__global__ void dact_mul_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out,
+                                long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float uu = __bfloat162float(u[i]);
+    float d = 1.0f;
+    if (ACT == 2) {  // SiLU
+        const float sg = 1.0f / (1.0f + __expf(-uu));
+        d = sg * fmaf(uu, 1.0f - sg, 1.0f);
+    }
+    out[i] = __float2bfloat16(g[i] * d);
 }
 
 }  // namespace jat

@@ -77,9 +77,18 @@ __device__ __forceinline__ float apply_act(float v) {
 // derivative of the activation at pre-activation u (backward of mlp.1 / patch_embed.proj.1 GELU, t_embedder.2 SiLU)
 template <int ACT>
 __device__ __forceinline__ float dact(float u) {
-    if constexpr (ACT == ACT_GELU) {  // d/du [u Phi(u)] = Phi(u) + u phi(u)
-        const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-        return fmaf(u * 0.3989422804014327f, __expf(-0.5f * u * u), cdf);
+    if constexpr (ACT == ACT_GELU) {  // d/du [u Phi(u)] = Phi(u) + u phi(u), Phi from the same A&S 7.1.26 form as gelu_erf
+        const float a = fabsf(u) * 0.84932180028801904f;  // |u| sqrt(log2(e) / 2)
+        float t, e;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27273748f, a, 1.0f)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * a));  // = exp(-u^2 / 2)
+        float pl = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+        pl = fmaf(t, pl, 0.5f * 1.421413741f);
+        pl = fmaf(t, pl, 0.5f * -0.284496736f);
+        pl = fmaf(t, pl, 0.5f * 0.254829592f);
+        const float q = pl * t * e;                        // 1 - Phi(|u|)
+        const float cdf = u >= 0.0f ? 1.0f - q : q;
+        return fmaf(u * 0.3989422804014327f, e, cdf);
     }
     if constexpr (ACT == ACT_SILU) {  // d/du [u sigma(u)] = sigma(u) (1 + u (1 - sigma(u)))
         const float sg = 1.0f / (1.0f + __expf(-u));

@@ -177,7 +177,8 @@ class TrainBuffers:
                           t_u2=bf(B, D))
         NM = depth * 6 * D
         self.scratch = dict(dx=f32(M, D), dy=bf(M, D), dh=bf(M, D), da=bf(M, D), du=bf(M, F), dqkv=bf(M, qkv),
-                            dsum=f32(B, Hq, N), dq_acc=f32(M, Hq * attn0.head_dim), dmod=f32(B, NM), dmod_bf16=bf(B, NM),
+                            dsum=f32(B, Hq, N), dq_acc=f32(M, Hq * attn0.head_dim), dmod=f32(depth, B, 6 * D),
+                            dmod_bf16=bf(depth, B, 6 * D), dt_acc=f32(B, D), rowstats=f32(M, 2),
                             dxsum=f32(B, D), dout_p=bf(M, Cc * P), dpe=bf(M, BD), dt_a=bf(B, D), dt_b=bf(B, D))
         self.sv, self.sc = L.DitSaved(), L.DitBwdScratch()
         for k_, v in self.saved.items():
@@ -295,16 +296,37 @@ class Engine:
         L.check(code)
         return out
 
-    def backward(self, d_out, B, T):
-        """d_out f32 [B, C, T] -> {parameter: f32 gradient view}; the saved activations of the last forward_train
-        with the same (B, T) are consumed."""
-        dev = d_out.device
-        lib, ctx = L.load(), L.context(self._dev_index(dev))
+    def _bwd_args(self, dev, B, T):
         pw, ws, tb = self.weights(dev), self.workspace(B, T, B, dev), self.train_buffers(B, T, dev)
         gr = self.grads(dev)
+        return (L.context(self._dev_index(dev)), C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), C.byref(tb.sc),
+                C.byref(gr.struct)), gr
+
+    def backward_begin(self, d_out, B, T):
+        """Stage 1 of the backward pass (final layer); zeroes the packed gradient buffers first."""
+        dev = d_out.device
+        args, gr = self._bwd_args(dev, B, T)
         gr.zero_()
-        L.check(lib.jat_dit_backward(ctx, C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), C.byref(tb.sc),
-                                     C.byref(gr.struct), d_out.data_ptr(), B, T, torch.cuda.current_stream(dev).cuda_stream))
+        L.check(L.load().jat_dit_backward_begin(*args, d_out.data_ptr(), B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return gr.by_param
+
+    def backward_block(self, i, B, T, dev):
+        args, gr = self._bwd_args(dev, B, T)
+        L.check(L.load().jat_dit_backward_block(*args, i, B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return gr.by_param
+
+    def backward_end(self, B, T, dev):
+        args, gr = self._bwd_args(dev, B, T)
+        L.check(L.load().jat_dit_backward_end(*args, B, T, torch.cuda.current_stream(dev).cuda_stream))
+        return gr.by_param
+
+    def backward(self, d_out, B, T):
+        """Whole backward in one call: d_out f32 [B, C, T] -> {parameter: f32 gradient view}; consumes the saved
+        activations of the last forward_train with the same (B, T)."""
+        dev = d_out.device
+        args, gr = self._bwd_args(dev, B, T)
+        gr.zero_()
+        L.check(L.load().jat_dit_backward(*args, d_out.data_ptr(), B, T, torch.cuda.current_stream(dev).cuda_stream))
         return gr.by_param
 
     def forward(self, x_t, t, x_cond, keep_blocks=False):

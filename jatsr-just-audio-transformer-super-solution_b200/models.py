@@ -19,25 +19,51 @@ from . import _lib as L
 from .engine import Engine
 
 
-class _DiTFunction(torch.autograd.Function):
-    """autograd node of the whole forward: forward = jat_dit_forward_train, backward = jat_dit_backward.  The
-    parameters are inputs of the node (so AdamW / GradScaler / clip_grad_norm_ / DDP hooks see ordinary .grad
-    tensors); x_t, t and x_cond get no gradient (the reference never differentiates them)."""
+class _Stage(torch.autograd.Function):
+    """The forward pass is ONE C-ABI call (`jat_dit_forward_train`, issued by the first stage); the autograd graph,
+    however, is a chain of stages  embed -> block 0 -> ... -> block depth-1 -> final  linked by a dummy token, each
+    stage taking its own parameters as inputs.  Its backward runs the matching `jat_dit_backward_{end,block,begin}`
+    and returns that stage's parameter gradients right away -- so DDP's bucketed all-reduce (train_ddp_v3mod2.py:822)
+    overlaps with the backward of the earlier blocks exactly as it does for the reference module, and AdamW /
+    GradScaler / clip_grad_norm_ see ordinary .grad tensors.  x_t, t and x_cond get no gradient (the reference never
+    differentiates them)."""
 
     @staticmethod
-    def forward(ctx, model, x_t, t, x_cond, *params):
-        ctx.model, ctx.shape = model, (x_t.shape[0], x_t.shape[2])
-        ctx.n_params = len(params)
-        return model._engine.forward_train(x_t, t, x_cond)
+    def forward(ctx, model, kind, index, token, payload, *params):
+        ctx.model, ctx.kind, ctx.index, ctx.params = model, kind, index, params
+        if kind == "embed":
+            x_t, t, x_cond = payload
+            ctx.shape = model._train_shape = (x_t.shape[0], x_t.shape[2], x_t.device)
+            model._train_out = model._engine.forward_train(x_t, t, x_cond)
+            return torch.zeros(1, device=x_t.device)
+        ctx.shape = model._train_shape
+        if kind == "final":
+            out, model._train_out = model._train_out, None
+            return out
+        return token.clone()
 
     @staticmethod
-    def backward(ctx, d_out):
-        model = ctx.model
-        B, T = ctx.shape
-        by_param = model._engine.backward(d_out.float().contiguous(), B, T)
-        # fresh tensors: autograd / DDP may keep or accumulate into what we return, the packed buffers are reused
-        grads = tuple(by_param[p].clone() if p.requires_grad else None for p in model.parameters())
-        return (None, None, None, None) + grads
+    def backward(ctx, grad):
+        model, (B, T, dev) = ctx.model, ctx.shape
+        eng = model._engine
+        if ctx.kind == "final":
+            by_param = eng.backward_begin(grad.float().contiguous(), B, T)
+        elif ctx.kind == "block":
+            by_param = eng.backward_block(ctx.index, B, T, dev)
+        else:
+            by_param = eng.backward_end(B, T, dev)
+        # fresh tensors: autograd / DDP keep (or accumulate into) what is returned, the packed buffers are reused
+        grads = tuple(by_param[p].clone() if p.requires_grad else None for p in ctx.params)
+        tok = None if ctx.kind == "embed" else torch.zeros(1, device=dev)
+        return (None, None, None, tok, None) + grads
+
+
+def _forward_train(model, x_t, t, x_cond):
+    embed = list(model.patch_embed.parameters()) + list(model.t_embedder.parameters())
+    tok = _Stage.apply(model, "embed", -1, None, (x_t, t, x_cond), *embed)
+    for i, blk in enumerate(model.blocks):
+        tok = _Stage.apply(model, "block", i, tok, None, *blk.parameters())
+    return _Stage.apply(model, "final", -1, tok, None, *model.final_layer.parameters())
 
 
 class TimeEmbedding(nn.Module):
@@ -172,7 +198,7 @@ class _JaTBase(nn.Module):
         self._check_inputs(x_t, t, x_cond)
         xt, tt, xc = x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous()
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            out = _DiTFunction.apply(self, xt, tt, xc, *self.parameters())
+            out = _forward_train(self, xt, tt, xc)
         else:
             out = self._engine.forward(xt, tt, xc)
         if torch.is_autocast_enabled():

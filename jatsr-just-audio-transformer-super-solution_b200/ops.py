@@ -161,9 +161,10 @@ def adaln_bwd(dh, x, B, tokens_per_batch, dx, *, scale=None, mod_batch_stride=0,
     _chk(x, torch.float32, "x")
     _chk(dx, torch.float32, "dx")
     D = x.shape[1]
+    rowstats = torch.empty(x.shape[0], 2, dtype=torch.float32, device=x.device)
     L.check(L.load().jat_adaln_bwd(_ctx(x), dh.data_ptr(), x.data_ptr(), _p(scale), mod_batch_stride, _p(weight), norm_kind,
                                    eps, dx.data_ptr(), int(accumulate), _p(dshift), _p(dscale), dmod_batch_stride,
-                                   _p(dweight), B, tokens_per_batch, D, _stream(x.device)))
+                                   _p(dweight), rowstats.data_ptr(), B, tokens_per_batch, D, _stream(x.device)))
     return dx
 
 

@@ -103,6 +103,53 @@ def bench_gemm(iters):
             report("cublas_fc1_shape_noepi", med, mn, flops=2.0 * m * n * k)
 
 
+def bench_bwd(iters):
+    """Backward-pass kernels at the training shapes (B = 28, M = 9660)."""
+    B, Ntok, D, F, QKV, Hq, Hkv = 28, 345, 1280, 5120, 1792, 20, 4
+    M = B * Ntok
+    bf = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
+    dh, x, dx = bf(M, D), torch.randn(M, D, device=dev), torch.randn(M, D, device=dev)
+    mod = torch.randn(B, 28 * 6 * D, device=dev)
+    dmod = torch.zeros(28, B, 6 * D, device=dev)
+    fn = lambda: ops.adaln_bwd(dh, x, B, Ntok, dx, scale=mod[:, D:2 * D], mod_batch_stride=mod.stride(0), dshift=dmod[0, :, :D],
+                               dscale=dmod[0, :, D:2 * D], dmod_batch_stride=6 * D)
+    med, mn = timeit(fn, iters)
+    report("adaln_bwd_layernorm", med, mn, bytes_=M * D * 14.0)
+    y, dy = bf(M, D), torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    fn = lambda: ops.gate_bwd(dx, y, mod[:, 2 * D:3 * D], B, Ntok, dmod[0, :, 2 * D:3 * D], mod_batch_stride=mod.stride(0),
+                              dmod_batch_stride=6 * D, dy=dy)
+    med, mn = timeit(fn, iters)
+    report("gate_bwd", med, mn, bytes_=M * D * 8.0)
+    du = bf(M, F)
+    out = torch.zeros(F, device=dev)
+    med, mn = timeit(lambda: ops.colsum_bf16(du, out), iters)
+    report("colsum_bf16_MxF", med, mn, bytes_=M * F * 2.0)
+    # GEMMs: dgrad fc2 (+GELU'), dgrad fc1, wgrad fc1 / fc2 / qkv / out_proj
+    W1, W2 = bf(F, D), bf(D, F)
+    u, h2 = bf(M, F), bf(M, D)
+    o_du, o_dh = torch.empty(M, F, dtype=torch.bfloat16, device=dev), torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    med, mn = timeit(lambda: ops.gemm(dh, W2, kind=L.EPI_DACT, act=L.ACT_GELU_ERF, aux=u, w_transposed=True, out=o_du), iters)
+    report("dgrad_fc2_dgelu", med, mn, flops=2.0 * M * F * D)
+    med, mn = timeit(lambda: ops.gemm(du, W1, w_transposed=True, out=o_dh), iters)
+    report("dgrad_fc1", med, mn, flops=2.0 * M * F * D)
+    for name, dY, X in (("wgrad_fc1", du, h2), ("wgrad_fc2", dh, u), ("wgrad_out_proj", dh, h2), ("wgrad_qkv", bf(M, QKV), h2)):
+        g = torch.zeros(dY.shape[1], X.shape[1], device=dev)
+        for ks in (1, 2, 4, 8):
+            med, mn = timeit(lambda: ops.gemm(dY, X, kind=L.EPI_ACCUM, out=g, a_transposed=True, w_transposed=True, k_splits=ks), iters)
+            report(name, med, mn, flops=2.0 * M * dY.shape[1] * X.shape[1], k_splits=ks)
+    # attention backward
+    qkv = bf(M, QKV)
+    lse = torch.empty(B, Hq, Ntok, device=dev)
+    o = ops.gqa_attention_fwd(qkv, B, Ntok, Hq, Hkv, lse=lse)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    emb = torch.outer(torch.arange(4096).float(), inv_freq)
+    emb = torch.cat([emb, emb], -1)
+    cos, sin = emb.cos().to(dev), emb.sin().to(dev)
+    dqkv = torch.empty_like(qkv)
+    med, mn = timeit(lambda: ops.gqa_attention_bwd(qkv, dh, o, lse, cos, sin, B, Ntok, Hq, Hkv, dqkv=dqkv), iters)
+    report("gqa_attention_bwd", med, mn, flops=2.5 * 4.0 * B * Hq * Ntok * Ntok * 64)
+
+
 def bench_attn(iters):
     B, N, Hq, Hkv = 56, 345, 20, 4
     qkv = torch.randn(B * N, (Hq + 2 * Hkv) * 64, device=dev).to(torch.bfloat16)
@@ -146,6 +193,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "gemm"):
         bench_gemm(a.iters)
+    if a.only in ("bwd",):
+        bench_bwd(a.iters)
     if a.only in ("", "attn"):
         bench_attn(a.iters)
     if a.only in ("", "elem"):
