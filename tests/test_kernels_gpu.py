@@ -434,14 +434,14 @@ def test_colsum_and_cast(ops):
 
 
 # ------------------------------------------------------------------------------------------------ attention backward
-def _rope_tables(npos):
+def _bwd_rope_tables(npos):
     inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=dev()).float() / 64))
     f = torch.outer(torch.arange(npos, device=dev()).float(), inv)
     e = torch.cat([f, f], -1)
     return e.cos().contiguous(), e.sin().contiguous()
 
 
-def _rope(x, cos, sin):  # x [B, N, H, 64]
+def _bwd_rope(x, cos, sin):  # x [B, N, H, 64]
     x1, x2 = x[..., :32], x[..., 32:]
     return x * cos[None, :, None, :] + torch.cat([-x2, x1], -1) * sin[None, :, None, :]
 
@@ -451,10 +451,10 @@ def test_gqa_attention_bwd_matches_autograd(ops, B, N, Hq, Hkv):
     """dqkv (w.r.t. the PRE-RoPE projections) vs torch autograd through RoPE + repeat_interleave + softmax attention."""
     torch.manual_seed(31)
     G = Hq // Hkv
-    cos, sin = _rope_tables(N)
+    cos, sin = _bwd_rope_tables(N)
     raw = (torch.randn(B, N, Hq + 2 * Hkv, 64, device=dev())).to(torch.bfloat16).float().requires_grad_(True)
-    q = _rope(raw[:, :, :Hq], cos, sin)
-    k = _rope(raw[:, :, Hq:Hq + Hkv], cos, sin)
+    q = _bwd_rope(raw[:, :, :Hq], cos, sin)
+    k = _bwd_rope(raw[:, :, Hq:Hq + Hkv], cos, sin)
     v = raw[:, :, Hq + Hkv:]
     # the kernels see bf16 RoPE'd projections (what the QKV GEMM epilogue stores)
     qkv = torch.cat([q, k, v], 2).detach().reshape(B * N, -1).to(torch.bfloat16)
