@@ -122,6 +122,12 @@ typedef struct jat_gemm_epilogue {
     int32_t w_transposed; /* 1: W is given as W^T [K, N] row-major with pitch ldw.  Backward GEMMs without copies:
                              dgrad dX = dY W      -> A = dY, W = weight with w_transposed = 1;
                              wgrad dW = dY^T X    -> A = dY with a_transposed = 1, W = X with w_transposed = 1 */
+    float drop_p;         /* train-mode nn.Dropout(p) fused into the epilogue (0 = off), element (m, n) of site drop_seed:
+                             BIAS_ACT/bf16: out = drop(act(acc + bias));  GATE_RESIDUAL: x += gate * drop(acc + bias) (aux
+                             keeps the dropped value);  DACT: out = (acc + bias) * mask * act'(aux)  (same mask as the
+                             forward BIAS_ACT call with the same seed) */
+    uint32_t drop_seed;   /* jat_dropout_site_seed(...) */
+    const float* gate_rowscale; /* GATE_RESIDUAL: optional f32 [B] factor on the gate per batch item (DropPath) or NULL */
 } jat_gemm_epilogue;
 
 /* cta_pair: 0 = one CTA per 128-row tile (tcgen05 cta_group::1), 1 = CTA pair per 256-row tile
@@ -142,13 +148,39 @@ int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64
 int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, float* lse_or_null, int B, int N, int Hq,
                           int Hkv, int head_dim, void* stream);
 
-/* Backward of jat_gqa_attention_fwd (dropout 0).  d_out / out bf16 [B*N, Hq*64] (gradient of, and the saved, forward
+/* Backward of jat_gqa_attention_fwd.  d_out / out bf16 [B*N, Hq*64] (gradient of, and the saved, forward
  * output), lse from the forward call.  Writes dqkv bf16 [B*N, (Hq+2Hkv)*64] = gradient w.r.t. the PRE-RoPE q | k | v
  * projections (the RoPE rotation of the QKV epilogue is transposed inside).  Scratch (caller-owned):
  * dsum_scratch f32 [B, Hq, N], dq_acc_scratch f32 [B*N, Hq*64].  rope_cos/sin: the forward's tables. */
 int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv_bf16, const void* d_out_bf16, const void* out_bf16, const float* lse,
                           float* dsum_scratch, float* dq_acc_scratch, void* dqkv_bf16, const float* rope_cos,
                           const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Train-mode stochastic regularisers.  The reference draws nn.Dropout(p) masks on the attention probabilities
+ * (jat_audiosr_v2.py:158), after the MLP's GELU (:250) and after mlp.3 (:252), and a per-sample DropPath factor on
+ * each gated branch (:21-34, :281, :287) from torch's global Philox stream.  Here every mask element is a pure function
+ * of (site seed, row, col): KEEP iff hash(row, col, site_seed) >= round(p * 2^32), kept values scaled by 1/(1-p) -- so the
+ * backward kernels regenerate the forward's masks instead of storing them, and the same Bernoulli(1-p) statistics hold.
+ * Site seeds: jat_dropout_site_seed(seed, block, site).  Mask coordinates: attention (row = (b*Hq + h)*N + query,
+ * col = key); MLP sites (row = token row m, col = feature).
+ * -------------------------------------------------------------------------------------------- */
+#define JAT_DROP_SITE_ATTN 0
+#define JAT_DROP_SITE_MLP_HIDDEN 1
+#define JAT_DROP_SITE_MLP_OUT 2
+#define JAT_DROP_SITE_PATH 3
+uint32_t jat_dropout_site_seed(uint64_t seed, int block, int site);
+/* out f32 [rows, cols] = the multiplier (0 or 1/(1-p)) the fused kernels apply at (row, col) of a site (parity tests). */
+int jat_dropout_scale_mask(jat_ctx* ctx, float* out, int64_t rows, int cols, float p, uint32_t site_seed, void* stream);
+/* DropPath factors: out f32 [depth, 2, B], out[i][branch][b] = floor(keep_i + U) / keep_i with keep_i = 1 - rates[i]
+ * (rates: DEVICE f32 [depth]; 1 where rates[i] == 0); branch 0 = attention, 1 = MLP. */
+int jat_drop_path_scales(jat_ctx* ctx, float* out, const float* rates, int depth, int B, uint64_t seed, void* stream);
+int jat_gqa_attention_fwd_dropout(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, float* lse_or_null, int B, int N,
+                                  int Hq, int Hkv, int head_dim, float drop_p, uint32_t drop_seed, void* stream);
+int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv_bf16, const void* d_out_bf16, const void* out_bf16,
+                                  const float* lse, float* dsum_scratch, float* dq_acc_scratch, void* dqkv_bf16,
+                                  const float* rope_cos, const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim,
+                                  float drop_p, uint32_t drop_seed, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Fused sampler update (infer_test_v3m2.py:161-179): CFG combine + x-prediction -> velocity + Euler.
@@ -223,8 +255,7 @@ int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit
                            int64_t mod_batch_stride, float* out, int B, int T, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
- * Training step (train_ddp_v3mod2.py:886 forward, :922 backward; dropout / DropPath must be 0 -- the reference's own
- * gradient semantics are only defined then).  `jat_dit_forward_train` = JaT_AudioSR_V2/V3.forward with
+ * Training step (train_ddp_v3mod2.py:886 forward, :922 backward).  `jat_dit_forward_train` = JaT_AudioSR_V2/V3.forward with
  * per-sample t, keeping in `saved` what the backward needs; `jat_dit_backward` = autograd of that forward: given
  * d_out = dL/d(out) f32 [B, C, T] it ACCUMULATES (+=) f32 parameter gradients into `grads`, a jat_dit_weights whose
  * pointers address f32 buffers with exactly the shapes of the (bf16 / f32) weights they mirror.  No gradient is
@@ -246,6 +277,12 @@ typedef struct jat_dit_saved {
     void* pe_u;   /* bf16 [M, bottleneck]  patch_embed.proj.0 pre-activation */
     void* t_u1;   /* bf16 [B, hidden]  t_embedder.1 pre-activation */
     void* t_u2;   /* bf16 [B, hidden]  t_emb (input of the adaLN SiLU) */
+    /* train-mode regularisers of this step (the backward regenerates the forward's masks from them) */
+    float dropout_p;               /* nn.Dropout p of the attention / MLP sites, 0 = off */
+    int32_t reserved;
+    uint64_t seed;                 /* step seed: every (block, site) mask derives from it */
+    const float* drop_path_rates;  /* DEVICE f32 [depth] DropPath.drop_prob per block, or NULL = no DropPath */
+    float* dp_scale;               /* f32 [depth, 2, B] per-sample DropPath factors (written by the forward) */
 } jat_dit_saved;
 
 typedef struct jat_dit_bwd_scratch {
@@ -326,6 +363,12 @@ int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float
 int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
                  void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
                  int tokens_per_batch, int D, void* stream);
+/* jat_gate_bwd with the forward's regularisers: y was dropout(acc + bias) with (drop_p, drop_seed) -- dy and dbias get the
+ * same mask -- and entered x as gate_rowscale[b] * gate_b * y (DropPath; NULL = 1). */
+int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
+                         void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
+                         int tokens_per_batch, int D, float drop_p, uint32_t drop_seed, const float* gate_rowscale,
+                         void* stream);
 int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream);
 int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream);
 

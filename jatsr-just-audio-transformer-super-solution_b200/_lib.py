@@ -27,6 +27,7 @@ EPI_BIAS_ACT, EPI_QKV_ROPE, EPI_GATE_RESIDUAL, EPI_UNPATCHIFY, EPI_ACCUM, EPI_DA
 ACT_NONE, ACT_GELU_ERF, ACT_SILU = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ERR_SEQ_TOO_LONG = -5
+DROP_SITE_ATTN, DROP_SITE_MLP_HIDDEN, DROP_SITE_MLP_OUT, DROP_SITE_PATH = 0, 1, 2, 3
 
 
 def _sources():
@@ -60,6 +61,7 @@ class GemmEpilogue(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_cols", C.c_int32), ("patch_len", C.c_int32), ("t_out", C.c_int32), ("k_splits", C.c_int32),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("a_transposed", C.c_int32), ("w_transposed", C.c_int32),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("gate_rowscale", C.c_void_p),
     ]
 
 
@@ -92,7 +94,9 @@ class DitWorkspace(C.Structure):
 
 class DitSaved(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x_in", "x_mid", "h1", "qkv", "attn", "lse", "y1", "h2", "u", "mact", "y2",
-                                          "pe_u", "t_u1", "t_u2")]
+                                          "pe_u", "t_u1", "t_u2")] + [
+        ("dropout_p", C.c_float), ("reserved", C.c_int32), ("seed", C.c_uint64),
+        ("drop_path_rates", C.c_void_p), ("dp_scale", C.c_void_p)]
 
 
 class DitBwdScratch(C.Structure):
@@ -101,8 +105,15 @@ class DitBwdScratch(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/jat_b200.h declares
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _u32, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 SIGNATURES = {
+    "jat_dropout_site_seed": (_u32, [_u64, _i, _i]),
+    "jat_dropout_scale_mask": (_i, [_vp, _vp, _i64, _i, _f, _u32, _vp]),
+    "jat_drop_path_scales": (_i, [_vp, _vp, _vp, _i, _i, _u64, _vp]),
+    "jat_gqa_attention_fwd_dropout": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32, _vp]),
+    "jat_gqa_attention_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32,
+                                           _vp]),
+    "jat_gate_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _f, _u32, _vp, _vp]),
     "jat_abi_version": (_i, []),
     "jat_last_error": (C.c_char_p, []),
     "jat_create": (_i, [_i, C.POINTER(_vp)]),

@@ -198,6 +198,49 @@ static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t ro
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+extern "C" uint32_t jat_dropout_site_seed(uint64_t seed, int block, int site) {
+    const uint64_t h = splitmix64(splitmix64(seed) ^ (((uint64_t)(uint32_t)block << 8) | (uint64_t)(uint32_t)(site & 0xff)));
+    return (uint32_t)(h >> 32) ^ (uint32_t)h;
+}
+// p -> DropCfg; returns false if p is outside [0, 1)
+static bool make_drop(float p, uint32_t seed, DropCfg* d) {
+    d->thresh = 0u; d->seed = seed; d->inv_keep = 1.0f;
+    if (!(p >= 0.0f) || p >= 1.0f) return false;
+    if (p == 0.0f) return true;
+    double th = (double)p * 4294967296.0;
+    d->thresh = th >= 4294967295.0 ? 4294967295u : (th < 1.0 ? 1u : (uint32_t)(th + 0.5));
+    d->inv_keep = 1.0f / (1.0f - p);
+    return true;
+}
+
+extern "C" int jat_dropout_scale_mask(jat_ctx* ctx, float* out, int64_t rows, int cols, float p, uint32_t site_seed,
+                                      void* stream) {
+    if (!ctx || !out || rows <= 0 || cols <= 0 || rows > 0xffffffffll) return fail(JAT_ERR_BAD_ARG, "jat_dropout_scale_mask: bad argument");
+    DropCfg d;
+    if (!make_drop(p, site_seed, &d)) return fail(JAT_ERR_BAD_ARG, "jat_dropout_scale_mask: p must be in [0, 1)");
+    const long long n = (long long)rows * cols;
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    dropout_scale_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, cols, d);
+    return post_launch(ctx, "dropout_scale_mask");
+}
+
+extern "C" int jat_drop_path_scales(jat_ctx* ctx, float* out, const float* rates, int depth, int B, uint64_t seed,
+                                    void* stream) {
+    if (!ctx || !out || !rates || depth <= 0 || B <= 0) return fail(JAT_ERR_BAD_ARG, "jat_drop_path_scales: bad argument");
+    const uint32_t s32 = jat_dropout_site_seed(seed, -1, JAT_DROP_SITE_PATH);
+    const int n = depth * 2 * B;
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    drop_path_scales_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, rates, depth, B, s32);
+    return post_launch(ctx, "drop_path_scales");
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM
 template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0>
 static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
@@ -302,6 +345,12 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     p.ldo = e->ldo;
     p.gate = e->gate;
     p.gate_bstride = e->gate_batch_stride;
+    p.gate_rowscale = e->gate_rowscale;
+    if (!make_drop(e->drop_p, e->drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: drop_p must be in [0, 1)");
+    if (p.drop.thresh != 0u && !(e->kind == JAT_EPI_GATE_RESIDUAL || e->kind == JAT_EPI_DACT ||
+                                 (e->kind == JAT_EPI_BIAS_ACT && e->out_dtype == JAT_DTYPE_BF16)))
+        return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: dropout is fused into the BIAS_ACT(bf16) / GATE_RESIDUAL / DACT epilogues only");
+    if (p.drop.thresh != 0u && e->k_splits > 1) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: dropout cannot be combined with k_splits");
     p.tokens_per_batch = e->tokens_per_batch > 0 ? e->tokens_per_batch : M;
     p.rope_cos = e->rope_cos;
     p.rope_sin = e->rope_sin;
@@ -508,6 +557,16 @@ extern "C" int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, 
 extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
                             void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
                             int tokens_per_batch, int D, void* stream) {
+    return jat_gate_bwd_dropout(ctx, dx, y_bf16, gate, mod_batch_stride, dy_bf16, dgate, dmod_batch_stride, dxsum_scratch,
+                                dbias, B, tokens_per_batch, D, 0.0f, 0u, nullptr, stream);
+}
+
+extern "C" int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate,
+                                    int64_t mod_batch_stride, void* dy_bf16, float* dgate, int64_t dmod_batch_stride,
+                                    float* dxsum_scratch, float* dbias, int B, int tokens_per_batch, int D, float drop_p,
+                                    uint32_t drop_seed, const float* gate_rowscale, void* stream) {
+    DropCfg drop;
+    if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: drop_p must be in [0, 1)");
     if (!ctx || !dx || !y_bf16 || !gate || !dy_bf16 || !dgate) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: null argument");
     if (dbias != nullptr && dxsum_scratch == nullptr) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: dbias needs the [B, D] scratch");
     if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
@@ -518,11 +577,11 @@ extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, c
     dim3 grid((tokens_per_batch + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block((D / 4 + 31) / 32 * 32);
     pre_launch(ctx, TAG_GATE_BWD, s);
     gate_bwd_kernel<<<grid, block, 0, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride, (__nv_bfloat16*)dy_bf16,
-                                           dgate, dmod_batch_stride, xs, D, tokens_per_batch);
+                                           dgate, dmod_batch_stride, xs, D, tokens_per_batch, drop, gate_rowscale);
     JAT_TRY(post_launch(ctx, "gate_bwd"));
     if (dbias) {
         pre_launch(ctx, TAG_GATE_BWD, s);
-        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D);
+        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D, gate_rowscale);
         return post_launch(ctx, "gate_bias_grad");
     }
     return 0;
@@ -591,7 +650,7 @@ extern "C" int jat_crossfade_denorm(jat_ctx* ctx, const float* chunks, int n_chu
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-template <int NKH>
+template <int NKH, bool DROP = false>
 static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv, uint64_t rows, uint64_t cols,
                             const AttnParams& p, dim3 grid, cudaStream_t s) {
     using Cfg = AttCfg<NKH>;
@@ -599,17 +658,22 @@ static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv
     JAT_TRY(make_tmap(ctx, &tkv, qkv, rows, cols, cols, (uint32_t)NKH));
     static bool configured = false;
     if (!configured) {
-        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel<NKH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel<NKH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
         configured = true;
     }
     pre_launch(ctx, TAG_ATTN, s);
-    gqa_attention_fwd_kernel<NKH><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tkv, p);
+    gqa_attention_fwd_kernel<NKH, DROP><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tkv, p);
     return post_launch(ctx, "gqa_attention_fwd");
 }
 
 extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq, int Hkv,
                                      int head_dim, void* stream) {
+    return jat_gqa_attention_fwd_dropout(ctx, qkv, out, lse, B, N, Hq, Hkv, head_dim, 0.0f, 0u, stream);
+}
+
+extern "C" int jat_gqa_attention_fwd_dropout(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq,
+                                             int Hkv, int head_dim, float drop_p, uint32_t drop_seed, void* stream) {
     if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
     if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
@@ -623,12 +687,21 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, f
     p.lse = lse;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.trace = ctx->att_trace;
+    if (!make_drop(drop_p, drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: drop_p must be in [0, 1)");
+    if ((long long)B * Hq * N > 0xffffffffll) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: B*Hq*N exceeds 2^32");
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
     cudaStream_t s = (cudaStream_t)stream;
     // key range padded to NK = 2*NKH columns (two softmax warpgroups); padded keys are masked in-kernel
+    if (p.drop.thresh != 0u) {
+        if (N <= 64) return launch_attention<32, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (N <= 128) return launch_attention<64, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (N <= 192) return launch_attention<96, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (N <= 256) return launch_attention<128, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        return launch_attention<176, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+    }
     if (N <= 64) return launch_attention<32>(ctx, tq, qkv, rows, cols, p, grid, s);
     if (N <= 128) return launch_attention<64>(ctx, tq, qkv, rows, cols, p, grid, s);
     if (N <= 192) return launch_attention<96>(ctx, tq, qkv, rows, cols, p, grid, s);
@@ -639,6 +712,14 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, f
 extern "C" int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv, const void* d_out, const void* out, const float* lse,
                                      float* dsum_scratch, float* dq_acc_scratch, void* dqkv, const float* rope_cos,
                                      const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, void* stream) {
+    return jat_gqa_attention_bwd_dropout(ctx, qkv, d_out, out, lse, dsum_scratch, dq_acc_scratch, dqkv, rope_cos, rope_sin, B, N,
+                                         Hq, Hkv, head_dim, 0.0f, 0u, stream);
+}
+
+extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, const void* d_out, const void* out, const float* lse,
+                                             float* dsum_scratch, float* dq_acc_scratch, void* dqkv, const float* rope_cos,
+                                             const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, float drop_p,
+                                             uint32_t drop_seed, void* stream) {
     if (!ctx || !qkv || !d_out || !out || !lse || !dsum_scratch || !dq_acc_scratch || !dqkv || !rope_cos || !rope_sin)
         return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_bwd: head_dim must be 64 (got %d)", head_dim);
@@ -664,6 +745,7 @@ extern "C" int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv, const void* 
     p.rope_cos = rope_cos; p.rope_sin = rope_sin;
     p.scale = 0.125f;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
+    if (!make_drop(drop_p, drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: drop_p must be in [0, 1)");
     static bool configured = false;
     if (!configured) {
         JAT_CUDA(cudaFuncSetAttribute(gqa_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTB_SMEM_BYTES));
@@ -764,7 +846,7 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
 
 
 // ------------------------------------------------------------------------------------------------ training step
-// Training-mode forward (dropout / DropPath = 0): the same kernels as jat_dit_forward_tokens, but every activation
+// Training-mode forward: the same kernels as jat_dit_forward_tokens, but every activation
 // the backward pass needs is kept in `sv` (per-block slabs, leading dimension = depth) instead of being overwritten.
 static jat_gemm_epilogue epi_plain(int kind, void* out, int64_t ldo) {
     jat_gemm_epilogue e;
@@ -786,6 +868,15 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
     const int QKV = (Hq + 2 * Hkv) * 64, KIN = 2 * C * P, NM = w->depth * 6 * D;
     cudaStream_t s = (cudaStream_t)stream;
     jat_gemm_epilogue e;
+    // ---- train-mode regularisers: Dropout(p) on attention probabilities / GELU output / mlp.3 output, DropPath per block
+    const float pd = sv->dropout_p;
+    if (!(pd >= 0.0f) || pd >= 1.0f) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_train: dropout_p must be in [0, 1)");
+    const float* dps = nullptr;  // [depth, 2, B] per-sample DropPath factors
+    if (sv->drop_path_rates != nullptr) {
+        if (!sv->dp_scale) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_train: drop_path_rates given without dp_scale");
+        JAT_TRY(jat_drop_path_scales(ctx, sv->dp_scale, sv->drop_path_rates, w->depth, B, sv->seed, stream));
+        dps = sv->dp_scale;
+    }
 
     // ---- timestep path with the pre-activations kept (t_embedder + adaLN_modulation of every block)
     JAT_TRY(jat_timestep_features(ctx, t, ws->t_feat, B, D, stream));
@@ -818,10 +909,12 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
         e.kind = JAT_EPI_QKV_ROPE; e.out = qkv; e.ldo = QKV; e.tokens_per_batch = N;
         e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (Hq + Hkv) * 64;
         JAT_TRY(jat_gemm_bf16(ctx, h1, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
-        JAT_TRY(jat_gqa_attention_fwd(ctx, qkv, attn, (float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), B, N, Hq, Hkv, 64, stream));
+        JAT_TRY(jat_gqa_attention_fwd_dropout(ctx, qkv, attn, (float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), B, N, Hq, Hkv, 64,
+                                              pd, jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
         e.gate = m + 2 * D; e.gate_batch_stride = NM; e.aux = at(sv->y1, i, MD, 2); e.ld_aux = D;
+        e.gate_rowscale = dps ? dps + (int64_t)(2 * i) * B : nullptr;
         JAT_TRY(jat_gemm_bf16(ctx, attn, D, w->wo[i], D, M, D, D, &e, -1, 0, stream));
 
         JAT_CUDA(cudaMemcpyAsync(at(sv->x_mid, i, MD, 4), ws->x, MD * 4, cudaMemcpyDeviceToDevice, s));
@@ -829,10 +922,13 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
                                         w->norm_kind, w->norm_eps, M, D, N, stream));
         e = epi_bias_act(w->b1[i], mact, F, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
         e.aux = at(sv->u, i, (int64_t)M * F, 2); e.ld_aux = F;
+        e.drop_p = pd; e.drop_seed = jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_HIDDEN);
         JAT_TRY(jat_gemm_bf16(ctx, h2, D, w->w1[i], D, M, F, D, &e, -1, 0, stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N; e.bias = w->b2[i];
         e.gate = m + 5 * D; e.gate_batch_stride = NM; e.aux = at(sv->y2, i, MD, 2); e.ld_aux = D;
+        e.drop_p = pd; e.drop_seed = jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_OUT);
+        e.gate_rowscale = dps ? dps + (int64_t)(2 * i + 1) * B : nullptr;
         JAT_TRY(jat_gemm_bf16(ctx, mact, F, w->w2[i], F, M, D, F, &e, -1, 0, stream));
     }
     // final layer: ws->x (input of the final norm) and ws->h (its output) stay valid until the backward pass
@@ -861,9 +957,10 @@ static int wgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* X, int
 }
 // input gradient  dX[Mtok, Kin] = dY[Mtok, Nout] W[Nout, Kin]  (W as stored), optional * act'(u)
 static int dgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* W, int Kin, int Nout, int Mtok, void* dX, int act,
-                 const void* u, void* stream) {
+                 const void* u, void* stream, float drop_p = 0.0f, uint32_t drop_seed = 0u) {
     jat_gemm_epilogue e = epi_plain(act == JAT_ACT_NONE ? JAT_EPI_BIAS_ACT : JAT_EPI_DACT, dX, Kin);
     e.act = act; e.w_transposed = 1; e.aux = const_cast<void*>(u); e.ld_aux = Kin;
+    e.drop_p = drop_p; e.drop_seed = drop_seed;
     return jat_gemm_bf16(ctx, dY, ld_dy, W, Kin, Mtok, Kin, Nout, &e, -1, 0, stream);
 }
 
@@ -918,24 +1015,29 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
     const void* h2 = at(sv->h2, i, MD, 2);
     const void* u = at(sv->u, i, (int64_t)M * F, 2);
     const void* mact = at(sv->mact, i, (int64_t)M * F, 2);
-    // ---- MLP branch: x2 = x1 + gate_mlp * (gelu(h2 W1^T + b1) W2^T + b2)
-    JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, d.SIXD, sc->dxsum,
-                         (float*)gr->b2[i], B, N, D, stream));
+    const float pd = sv->dropout_p;
+    const float* dps = sv->drop_path_rates != nullptr ? sv->dp_scale : nullptr;
+    // ---- MLP branch: x2 = x1 + drop_path(gate_mlp * drop(drop(gelu(h2 W1^T + b1)) W2^T + b2))
+    JAT_TRY(jat_gate_bwd_dropout(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, d.SIXD, sc->dxsum,
+                                 (float*)gr->b2[i], B, N, D, pd, jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_OUT),
+                                 dps ? dps + (int64_t)(2 * i + 1) * B : nullptr, stream));
     JAT_TRY(wgrad(ctx, sc->dy, D, mact, F, (float*)gr->w2[i], D, F, M, stream));
-    JAT_TRY(dgrad(ctx, sc->dy, D, w->w2[i], F, D, M, sc->du, JAT_ACT_GELU_ERF, u, stream));
+    JAT_TRY(dgrad(ctx, sc->dy, D, w->w2[i], F, D, M, sc->du, JAT_ACT_GELU_ERF, u, stream, pd,
+                  jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_HIDDEN)));
     JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
     JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
     JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
                           w->norm_kind, w->norm_eps, sc->dx, 1, dm + 3 * D, dm + 4 * D, d.SIXD,
                           rms ? (float*)gr->norm2_w[i] : nullptr, sc->rowstats, B, N, D, stream));
-    // ---- attention branch: x1 = x + gate_msa * (attn(h1) Wo^T)
-    JAT_TRY(jat_gate_bwd(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, d.SIXD, nullptr, nullptr, B, N, D,
-                         stream));
+    // ---- attention branch: x1 = x + drop_path(gate_msa * (attn(h1) Wo^T))
+    JAT_TRY(jat_gate_bwd_dropout(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, d.SIXD, nullptr, nullptr,
+                                 B, N, D, 0.0f, 0u, dps ? dps + (int64_t)(2 * i) * B : nullptr, stream));
     JAT_TRY(wgrad(ctx, sc->dy, D, attn, D, (float*)gr->wo[i], D, D, M, stream));
     JAT_TRY(dgrad(ctx, sc->dy, D, w->wo[i], D, D, M, sc->da, JAT_ACT_NONE, nullptr, stream));
-    JAT_TRY(jat_gqa_attention_bwd(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * d.Hq * N, 4), sc->dsum,
-                                  sc->dq_acc, sc->dqkv, w->rope_cos, w->rope_sin, B, N, d.Hq, d.Hkv, 64, stream));
+    JAT_TRY(jat_gqa_attention_bwd_dropout(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * d.Hq * N, 4), sc->dsum,
+                                          sc->dq_acc, sc->dqkv, w->rope_cos, w->rope_sin, B, N, d.Hq, d.Hkv, 64, pd,
+                                          jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
     JAT_TRY(wgrad(ctx, sc->dqkv, d.QKV, h1, D, (float*)gr->wqkv[i], d.QKV, D, M, stream));
     JAT_TRY(dgrad(ctx, sc->dqkv, d.QKV, w->wqkv[i], D, d.QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
     JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,

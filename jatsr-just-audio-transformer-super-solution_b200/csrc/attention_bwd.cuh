@@ -40,6 +40,7 @@ struct AttnBwdParams {
     const float* rope_cos;  // [max_pos, 64]
     const float* rope_sin;
     float scale_log2e, scale;
+    DropCfg drop;  // the forward's dropout on the probabilities
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
@@ -240,8 +241,16 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                         p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2e, -lse_t[c * 32 + j]));
                         p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2e, -lse_t[c * 32 + j + 1]));
                     }
-                    const float d0 = p0 * (__uint_as_float(dv[j]) - ds_t[c * 32 + j]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(dv[j + 1]) - ds_t[c * 32 + j + 1]) * p.scale;
+                    float m0 = 1.0f, m1 = 1.0f;
+                    if (p.drop.thresh != 0u) {  // forward: O = (P * mask / keep) V   ->   dV uses P * m, dP = (dO V^T) * m
+                        const uint32_t rq = (uint32_t)(((long long)b * p.Hq + h) * p.N + qt * ATTB_TILE + c * 32 + j);
+                        m0 = drop_scale(p.drop, rq, (uint32_t)key);
+                        m1 = drop_scale(p.drop, rq + 1u, (uint32_t)key);
+                    }
+                    const float d0 = p0 * (__uint_as_float(dv[j]) * m0 - ds_t[c * 32 + j]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(dv[j + 1]) * m1 - ds_t[c * 32 + j + 1]) * p.scale;
+                    p0 *= m0;
+                    p1 *= m1;
                     pp[j >> 1] = pack_bf16(p0, p1);
                     dd[j >> 1] = pack_bf16(d0, d1);
                 }

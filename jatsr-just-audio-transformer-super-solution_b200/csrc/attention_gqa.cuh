@@ -65,6 +65,8 @@ struct AttnParams {
     float* lse;         // optional f32 [B, Hq, N]: log2-domain log-sum-exp of the scaled scores (kept for the backward pass)
     float scale_log2e;  // (1/sqrt(64)) * log2(e)
     long long* trace;   // debug: per-event clock64 timestamps of CTA (0,0,0), or NULL
+    DropCfg drop;       // train-mode dropout on the probabilities (jat_audiosr_v2.py:158): P.V uses P * mask / keep, the
+                        // softmax normaliser the undropped P; mask element = ((b*Hq + h)*N + query, key)
 };
 #define ATT_TRACE(slot)                                                                                    \
     do {                                                                                                   \
@@ -84,7 +86,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-template <int NKH>
+template <int NKH, bool DROP = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                          const AttnParams p) {
@@ -282,6 +284,8 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const float sl2 = p.scale_log2e;
         const int col0 = half * NKH;
         const bool trace_thr = (threadIdx.x & 127) == 0;
+        // dropout mask row of (b, first head of the group, this query); + h * N per head
+        const uint32_t drop_row = (uint32_t)(((long long)b * p.Hq + g * p.G) * p.N + qt * ATT_BQ + r);
 #pragma unroll 1
         for (int h = 0; h < p.G; ++h) {
             mbar_wait(&bar_s_full[half], (uint32_t)(h & 1));
@@ -329,8 +333,16 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const float e2 = ex2_approx(fmaf(__uint_as_float(s[j + 2]), sl2, -moff));
                 const float e3 = ex2_approx(fmaf(__uint_as_float(s[j + 3]), sl2, -moff));
                 a4[0] += e0; a4[1] += e1; a4[2] += e2; a4[3] += e3;
-                pk[j / 2] = pack_bf16(e0, e1);
-                pk[j / 2 + 1] = pack_bf16(e2, e3);
+                if constexpr (DROP) {
+                    const uint32_t kc = (uint32_t)(col0 + j);
+                    pk[j / 2] = pack_bf16(e0 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc),
+                                          e1 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 1));
+                    pk[j / 2 + 1] = pack_bf16(e2 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 2),
+                                              e3 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 3));
+                } else {
+                    pk[j / 2] = pack_bf16(e0, e1);
+                    pk[j / 2 + 1] = pack_bf16(e2, e3);
+                }
             }
             if (trace_thr) ATT_TRACE(32 + 32 * half + 4 * h + 2);
             // ---- P_half(h-1) V_half must have retired before its columns are overwritten (this also orders the

@@ -173,11 +173,14 @@ adaln_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dh, const float* __res
 __global__ void __launch_bounds__(512)
 gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
                 long long mod_bstride, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dmod_bstride,
-                float* __restrict__ dxsum, int D, int tokens_per_batch) {
+                float* __restrict__ dxsum, int D, int tokens_per_batch, DropCfg drop, const float* __restrict__ rowscale) {
     const int c4 = threadIdx.x;  // vec4 column
     if (c4 >= (D >> 2)) return;
     const int b = blockIdx.y;
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride) + c4);
+    // DropPath (jat_audiosr_v2.py:281,287): the branch entered x as (rowscale_b * gate_b) * y
+    const float rs = rowscale != nullptr ? __ldg(rowscale + b) : 1.0f;
+    float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride) + c4);
+    g4.x *= rs; g4.y *= rs; g4.z *= rs; g4.w *= rs;
     float4 a_gate = make_float4(0.f, 0.f, 0.f, 0.f), a_sum = a_gate;
     const int n0 = blockIdx.x * BWD_ROWS_PER_CTA;
     const int n1 = min(n0 + BWD_ROWS_PER_CTA, tokens_per_batch);
@@ -188,11 +191,18 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
         const float4 d = __ldcs(reinterpret_cast<const float4*>(dx + off) + c4);
         const float4 yv = bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(y + off) + c4));
         a_gate.x += d.x * yv.x; a_gate.y += d.y * yv.y; a_gate.z += d.z * yv.z; a_gate.w += d.w * yv.w;
-        a_sum.x += d.x; a_sum.y += d.y; a_sum.z += d.z; a_sum.w += d.w;
-        reinterpret_cast<uint2*>(dy + off)[c4] = make_uint2(pack_bf16(d.x * g4.x, d.y * g4.y), pack_bf16(d.z * g4.z, d.w * g4.w));
+        float4 dm = d;
+        if (drop.thresh != 0u) {  // forward: y = dropout(acc + bias) entered x through the gate
+            const uint32_t rr = (uint32_t)(row0 + n), cc = (uint32_t)(c4 * 4);
+            dm.x *= drop_scale(drop, rr, cc); dm.y *= drop_scale(drop, rr, cc + 1);
+            dm.z *= drop_scale(drop, rr, cc + 2); dm.w *= drop_scale(drop, rr, cc + 3);
+        }
+        a_sum.x += dm.x; a_sum.y += dm.y; a_sum.z += dm.z; a_sum.w += dm.w;
+        const float4 o = make_float4(dm.x * g4.x, dm.y * g4.y, dm.z * g4.z, dm.w * g4.w);
+        reinterpret_cast<uint2*>(dy + off)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     }
     float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
-    atomicAdd(dg, a_gate.x); atomicAdd(dg + 1, a_gate.y); atomicAdd(dg + 2, a_gate.z); atomicAdd(dg + 3, a_gate.w);
+    atomicAdd(dg, a_gate.x * rs); atomicAdd(dg + 1, a_gate.y * rs); atomicAdd(dg + 2, a_gate.z * rs); atomicAdd(dg + 3, a_gate.w * rs);
     if (dxsum != nullptr) {
         float* ds = dxsum + (long long)b * D + c4 * 4;
         atomicAdd(ds, a_sum.x); atomicAdd(ds + 1, a_sum.y); atomicAdd(ds + 2, a_sum.z); atomicAdd(ds + 3, a_sum.w);
@@ -201,11 +211,12 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
 
 // db[d] += sum_b gate[b, d] * dxsum[b, d]      (bias of mlp.3: y = acc + bias enters x through the gate)
 __global__ void gate_bias_grad_kernel(const float* __restrict__ gate, long long mod_bstride, const float* __restrict__ dxsum,
-                                      float* __restrict__ dbias, int B, int D) {
+                                      float* __restrict__ dbias, int B, int D, const float* __restrict__ rowscale) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += gate[(long long)b * mod_bstride + d] * dxsum[(long long)b * D + d];
+    for (int b = 0; b < B; ++b)
+        s += gate[(long long)b * mod_bstride + d] * (rowscale != nullptr ? rowscale[b] : 1.0f) * dxsum[(long long)b * D + d];
     dbias[d] += s;
 }
 

@@ -315,6 +315,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_major
            ((uint32_t)(m >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------------- dropout RNG
+// Counter-based Bernoulli masks for train-mode Dropout (jat_audiosr_v2.py:158, 250, 252): element (row, col) of
+// site `seed` is KEPT iff hash(row, col, seed) >= thresh, thresh = round(p * 2^32).  Stateless, so the backward
+// kernels regenerate exactly the forward's mask from the same (row, col, seed); tests rebuild it in torch.
+__host__ __device__ __forceinline__ uint32_t jat_hash3(uint32_t row, uint32_t col, uint32_t seed) {
+    uint32_t h = (row * 0x9E3779B1u) ^ ((col + seed) * 0x85EBCA77u);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+struct DropCfg {
+    uint32_t thresh;  // 0 = dropout off
+    uint32_t seed;
+    float inv_keep;   // 1 / (1 - p)
+};
+__device__ __forceinline__ float drop_scale(const DropCfg& d, uint32_t row, uint32_t col) {
+    return jat_hash3(row, col, d.seed) >= d.thresh ? d.inv_keep : 0.0f;
+}
+
 // ----------------------------------------------------------------------------------- math / packing
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -197,4 +197,32 @@ cfg_euler_update_kernel(float* __restrict__ z, const float* __restrict__ x_c, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Train-mode stochastic regularisers (nn.Dropout jat_audiosr_v2.py:158,250,252; DropPath :21-34).
+// dropout_scale_mask: materialises the multiplier matrix (0 or 1/keep) the fused kernels apply at element (row, col)
+// of a site -- used by the parity tests to rebuild the forward's masks in torch.
+// drop_path_scales: out[(i*2 + branch)*B + b] = floor(keep_i + U) / keep_i, the per-sample factor the reference
+// multiplies onto gate * branch of block i (1 when rates[i] == 0).
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_scale_mask_kernel(float* __restrict__ out, long long n, int cols, DropCfg d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = d.thresh != 0u ? drop_scale(d, (uint32_t)(i / cols), (uint32_t)(i % cols)) : 1.0f;
+}
+
+__global__ void drop_path_scales_kernel(float* __restrict__ out, const float* __restrict__ rates, int depth, int B,
+                                        uint32_t seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= depth * 2 * B) return;
+    const int site = i / B, b = i - site * B;
+    const float r = rates[site >> 1];
+    float v = 1.0f;
+    if (r > 0.0f) {
+        const double th = (double)r * 4294967296.0;
+        const uint32_t thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)(th + 0.5);
+        v = jat_hash3((uint32_t)b, (uint32_t)site, seed) >= thresh ? 1.0f / (1.0f - r) : 0.0f;
+    }
+    out[i] = v;
+}
+
 }  // namespace jat

@@ -37,12 +37,15 @@ struct GemmParams {
     long long ldo;
     const float* gate;
     long long gate_bstride;
+    const float* gate_rowscale;  // GATE_RESIDUAL: optional per-batch-item factor on the gate (DropPath), f32 [B] or NULL
     int tokens_per_batch;
     const float* rope_cos;
     const float* rope_sin;
     int rope_cols;
     int t_out;
     int k_splits;            // split-K: every output tile is computed by k_splits work items (reduce-add epilogues only)
+    DropCfg drop;            // train-mode dropout on the epilogue output (BIAS_ACT: after the activation; GATE_RESIDUAL:
+                             // on acc + bias before the gate; DACT: the same mask applied to the incoming gradient)
     const void* aux;         // EPI_DACT: pre-activation u bf16 [M, ld_aux];  EPI_BIAS_ACT: optional bf16 copy of (acc + bias)
     long long ld_aux;
 };
@@ -305,6 +308,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     f[2 * q] *= dact<ACT>(__uint_as_float(uw[q] << 16));
                                     f[2 * q + 1] *= dact<ACT>(__uint_as_float(uw[q] & 0xffff0000u));
                                 }
+                                if (p.drop.thresh != 0u) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) f[q] *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q));
+                                }
                             } else {
                                 if (use_aux)
                                     *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(aux_row) + n0 + hx * 32 + j) =
@@ -312,6 +319,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                                    pack_bf16(f[6], f[7]));
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) f[q] = apply_act<ACT>(f[q]);
+                                if (p.drop.thresh != 0u) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) f[q] *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q));
+                                }
                             }
                             st_slab_chunk(slab_row[buf], lane, hx * 4 + j / 8, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
                                           pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -329,8 +340,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // f32 slabs of 32 columns.  GATE_RESIDUAL: slab = gate * (acc + bias), TMA-reduce-added into x.
                 // ACCUM: slab = acc (+ bias), TMA-reduce-added into out (gradient accumulation, split-K partial sums).
                 const float* grow = nullptr;
-                if constexpr (EPI == EPI_GATE_RESIDUAL)
-                    grow = p.gate + (long long)(row_ok ? (m / p.tokens_per_batch) : 0) * p.gate_bstride;
+                float gsc = 1.0f;
+                if constexpr (EPI == EPI_GATE_RESIDUAL) {
+                    const int bi = row_ok ? (m / p.tokens_per_batch) : 0;
+                    grow = p.gate + (long long)bi * p.gate_bstride;
+                    if (p.gate_rowscale != nullptr) gsc = __ldg(p.gate_rowscale + bi);
+                }
 #pragma unroll 1
                 for (int sl = 0; sl < HALF / 32; ++sl) {
                     const int n0 = n_base + sl * 32;
@@ -346,12 +361,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
                               r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
                         if constexpr (EPI == EPI_GATE_RESIDUAL) {
+                            if (p.drop.thresh != 0u) {
+                                r0 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j));
+                                r1 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 1));
+                                r2 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 2));
+                                r3 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 3));
+                            }
                             if (p.aux != nullptr && row_ok)  // training forward keeps y = acc + bias (bf16) for the gate gradient
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.aux)) +
                                                           (long long)m * p.ld_aux + n0 + j) =
                                     make_uint2(pack_bf16(r0, r1), pack_bf16(r2, r3));
                             const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
-                            r0 *= g4.x; r1 *= g4.y; r2 *= g4.z; r3 *= g4.w;
+                            r0 *= g4.x * gsc; r1 *= g4.y * gsc; r2 *= g4.z * gsc; r3 *= g4.w * gsc;
                         } else if constexpr (EPI == EPI_BIAS_ACT) {
                             r0 = apply_act<ACT>(r0); r1 = apply_act<ACT>(r1); r2 = apply_act<ACT>(r2); r3 = apply_act<ACT>(r3);
                         }

@@ -180,9 +180,15 @@ class TrainBuffers:
                             dsum=f32(B, Hq, N), dq_acc=f32(M, Hq * attn0.head_dim), dmod=f32(depth, B, 6 * D),
                             dmod_bf16=bf(depth, B, 6 * D), dt_acc=f32(B, D), rowstats=f32(M, 2),
                             dxsum=f32(B, D), dout_p=bf(M, Cc * P), dpe=bf(M, BD), dt_a=bf(B, D), dt_b=bf(B, D))
+        # train-mode regularisers: per-block DropPath rates (the reference's linspace, jat_audiosr_v2.py:351) and factors
+        rates = [float(getattr(b.drop_path, "drop_prob", 0.0)) for b in model.blocks]
+        self.dp_rates = torch.tensor(rates, dtype=torch.float32, device=device) if any(r > 0 for r in rates) else None
+        self.dp_scale = f32(depth, 2, B) if self.dp_rates is not None else None
         self.sv, self.sc = L.DitSaved(), L.DitBwdScratch()
         for k_, v in self.saved.items():
             setattr(self.sv, k_, v.data_ptr())
+        self.sv.drop_path_rates = self.dp_rates.data_ptr() if self.dp_rates is not None else None
+        self.sv.dp_scale = self.dp_scale.data_ptr() if self.dp_rates is not None else None
         for k_, v in self.scratch.items():
             setattr(self.sc, k_, v.data_ptr())
 
@@ -280,13 +286,16 @@ class Engine:
             self._grads = PackedGrads(self.model, device)
         return self._grads
 
-    def forward_train(self, x_t, t, x_cond):
+    def forward_train(self, x_t, t, x_cond, dropout_p=0.0, seed=0):
+        """dropout_p / seed: this step's train-mode Dropout probability and mask seed (DropPath rates come from the
+        blocks); they are stored next to the saved activations so that the backward regenerates the same masks."""
         B, Cc, T = x_t.shape
         dev = x_t.device
         lib, ctx = L.load(), L.context(self._dev_index(dev))
         pw = self.weights(dev)
         ws = self.workspace(B, T, B, dev)
         tb = self.train_buffers(B, T, dev)
+        tb.sv.dropout_p, tb.sv.seed = float(dropout_p), int(seed)
         out = torch.empty(B, Cc, T, dtype=torch.float32, device=dev)
         code = lib.jat_dit_forward_train(ctx, C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), x_t.data_ptr(),
                                          x_cond.data_ptr(), t.data_ptr(), out.data_ptr(), B, T,

@@ -34,7 +34,13 @@ class _Stage(torch.autograd.Function):
         if kind == "embed":
             x_t, t, x_cond = payload
             ctx.shape = model._train_shape = (x_t.shape[0], x_t.shape[2], x_t.device)
-            model._train_out = model._engine.forward_train(x_t, t, x_cond)
+            # one draw from torch's global generator per step seeds every Dropout / DropPath mask of the step
+            # (the reference draws its masks from the same generator, so torch.manual_seed controls both)
+            p_drop = float(model.dropout_p)
+            stochastic = p_drop > 0.0 or model.drop_path_rate > 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) if stochastic else 0
+            model._train_seed = seed  # parity tests rebuild the step's masks from it
+            model._train_out = model._engine.forward_train(x_t, t, x_cond, dropout_p=p_drop, seed=seed)
             return torch.zeros(1, device=x_t.device)
         ctx.shape = model._train_shape
         if kind == "final":
@@ -186,9 +192,8 @@ class _JaTBase(nn.Module):
             raise NotImplementedError("cond_channels != input_channels is not supported by the fused patchify")
         if t.dim() != 1 or t.shape[0] != x_t.shape[0]:
             raise ValueError("t must be [B]")
-        if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError("train-mode Dropout / DropPath is not implemented by the CUDA path yet: build the "
-                                      "model with dropout=0.0, drop_path_rate=0.0 (or call model.eval())")
+        if not 0.0 <= self.dropout_p < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), got {self.dropout_p}")
         N = (x_t.shape[-1] + self.patch_len - 1) // self.patch_len
         if N > self.max_len:
             raise ValueError(f"Sequence length {N} exceeds max_len {self.max_len}")

@@ -73,7 +73,8 @@ def timestep_features(t, D, out=None):
 
 def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, bias=None, out=None,
          gate=None, gate_batch_stride=0, tokens_per_batch=0, rope_cos=None, rope_sin=None, rope_cols=0,
-         patch_len=4, t_out=0, cta_pair=-1, block_n=0, aux=None, k_splits=0, a_transposed=False, w_transposed=False):
+         patch_len=4, t_out=0, cta_pair=-1, block_n=0, aux=None, k_splits=0, a_transposed=False, w_transposed=False,
+         drop_p=0.0, drop_seed=0, gate_rowscale=None):
     """acc = A[M,K] @ W[N,K]^T (bf16 in, f32 accumulate) + fused epilogue; returns `out`.
     a_transposed / w_transposed: the tensor passed holds A^T [K, M] / W^T [K, N] (backward GEMMs, no copies)."""
     _chk(A, torch.bfloat16, "A")
@@ -98,19 +99,42 @@ def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, b
     e.patch_len, e.t_out, e.k_splits = patch_len, t_out, k_splits
     e.aux, e.ld_aux = _p(aux), (aux.stride(0) if aux is not None else 0)
     e.a_transposed, e.w_transposed = int(a_transposed), int(w_transposed)
+    e.drop_p, e.drop_seed, e.gate_rowscale = float(drop_p), int(drop_seed), _p(gate_rowscale)
     L.check(L.load().jat_gemm_bf16(_ctx(A), A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K,
                                    C.byref(e), cta_pair, block_n, _stream(A.device)))
     return out
 
 
-def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None):
-    """lse: optional f32 [B, Hq, N] output (log2-domain log-sum-exp per query row, for the backward pass)."""
+def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None, drop_p=0.0, drop_seed=0):
+    """lse: optional f32 [B, Hq, N] output (log2-domain log-sum-exp per query row, for the backward pass).
+    drop_p / drop_seed: train-mode dropout on the probabilities (mask row = (b*Hq + h)*N + query, col = key)."""
     _chk(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (B * N, (Hq + 2 * Hkv) * head_dim)
     if out is None:
         out = torch.empty(B * N, Hq * head_dim, dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().jat_gqa_attention_fwd(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, Hq, Hkv, head_dim,
-                                           _stream(qkv.device)))
+    L.check(L.load().jat_gqa_attention_fwd_dropout(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, Hq, Hkv,
+                                                   head_dim, float(drop_p), int(drop_seed), _stream(qkv.device)))
+    return out
+
+
+def dropout_site_seed(seed, block, site):
+    return int(L.load().jat_dropout_site_seed(int(seed), int(block), int(site)))
+
+
+def dropout_scale_mask(rows, cols, p, site_seed, device):
+    """f32 [rows, cols]: the multiplier (0 or 1/(1-p)) the fused kernels apply at (row, col) of a dropout site."""
+    out = torch.empty(rows, cols, dtype=torch.float32, device=device)
+    L.check(L.load().jat_dropout_scale_mask(_ctx(out), out.data_ptr(), rows, cols, float(p), int(site_seed),
+                                            _stream(out.device)))
+    return out
+
+
+def drop_path_scales(rates, B, seed):
+    """rates f32 [depth] (device) -> f32 [depth, 2, B] per-sample DropPath factors (branch 0 = attention, 1 = MLP)."""
+    _chk(rates, torch.float32, "rates")
+    out = torch.empty(rates.shape[0], 2, B, dtype=torch.float32, device=rates.device)
+    L.check(L.load().jat_drop_path_scales(_ctx(rates), out.data_ptr(), rates.data_ptr(), rates.shape[0], B, int(seed),
+                                          _stream(rates.device)))
     return out
 
 
@@ -168,16 +192,18 @@ def adaln_bwd(dh, x, B, tokens_per_batch, dx, *, scale=None, mod_batch_stride=0,
     return dx
 
 
-def gate_bwd(dx, y, gate, B, tokens_per_batch, dgate, *, mod_batch_stride=0, dmod_batch_stride=0, dbias=None, dy=None):
+def gate_bwd(dx, y, gate, B, tokens_per_batch, dgate, *, mod_batch_stride=0, dmod_batch_stride=0, dbias=None, dy=None,
+             drop_p=0.0, drop_seed=0, gate_rowscale=None):
     _chk(dx, torch.float32, "dx")
     _chk(y, torch.bfloat16, "y")
     D = dx.shape[1]
     if dy is None:
         dy = torch.empty_like(y)
     scratch = torch.empty(B, D, dtype=torch.float32, device=dx.device) if dbias is not None else None
-    L.check(L.load().jat_gate_bwd(_ctx(dx), dx.data_ptr(), y.data_ptr(), gate.data_ptr(), mod_batch_stride, dy.data_ptr(),
-                                  dgate.data_ptr(), dmod_batch_stride, _p(scratch), _p(dbias), B, tokens_per_batch, D,
-                                  _stream(dx.device)))
+    L.check(L.load().jat_gate_bwd_dropout(_ctx(dx), dx.data_ptr(), y.data_ptr(), gate.data_ptr(), mod_batch_stride,
+                                          dy.data_ptr(), dgate.data_ptr(), dmod_batch_stride, _p(scratch), _p(dbias), B,
+                                          tokens_per_batch, D, float(drop_p), int(drop_seed), _p(gate_rowscale),
+                                          _stream(dx.device)))
     return dy
 
 
@@ -196,7 +222,8 @@ def cast_f32_bf16(x, out=None):
     return out
 
 
-def gqa_attention_bwd(qkv, d_out, out, lse, rope_cos, rope_sin, B, N, Hq, Hkv, head_dim=64, dqkv=None):
+def gqa_attention_bwd(qkv, d_out, out, lse, rope_cos, rope_sin, B, N, Hq, Hkv, head_dim=64, dqkv=None, drop_p=0.0,
+                      drop_seed=0):
     """Gradient w.r.t. the pre-RoPE packed q|k|v projections, bf16 [B*N, (Hq+2Hkv)*64]."""
     for t, n in ((qkv, "qkv"), (d_out, "d_out"), (out, "out")):
         _chk(t, torch.bfloat16, n)
@@ -205,7 +232,8 @@ def gqa_attention_bwd(qkv, d_out, out, lse, rope_cos, rope_sin, B, N, Hq, Hkv, h
         dqkv = torch.empty_like(qkv)
     dsum = torch.empty(B, Hq, N, dtype=torch.float32, device=qkv.device)
     dq_acc = torch.empty(B * N, Hq * head_dim, dtype=torch.float32, device=qkv.device)
-    L.check(L.load().jat_gqa_attention_bwd(_ctx(qkv), qkv.data_ptr(), d_out.data_ptr(), out.data_ptr(), lse.data_ptr(),
-                                           dsum.data_ptr(), dq_acc.data_ptr(), dqkv.data_ptr(), rope_cos.data_ptr(),
-                                           rope_sin.data_ptr(), B, N, Hq, Hkv, head_dim, _stream(qkv.device)))
+    L.check(L.load().jat_gqa_attention_bwd_dropout(_ctx(qkv), qkv.data_ptr(), d_out.data_ptr(), out.data_ptr(),
+                                                   lse.data_ptr(), dsum.data_ptr(), dq_acc.data_ptr(), dqkv.data_ptr(),
+                                                   rope_cos.data_ptr(), rope_sin.data_ptr(), B, N, Hq, Hkv, head_dim,
+                                                   float(drop_p), int(drop_seed), _stream(qkv.device)))
     return dqkv

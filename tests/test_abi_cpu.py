@@ -18,7 +18,7 @@ def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|void|int64_t|const char\*)\s+(jat_\w+)\s*\(([^;{]*)\)\s*;", src):
+    for m in re.finditer(r"\b(?:int|void|int64_t|uint32_t|const char\*)\s+(jat_\w+)\s*\(([^;{]*)\)\s*;", src):
         args = m.group(2).strip()
         decls[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
     return decls
@@ -52,15 +52,19 @@ def test_structs_match_header_layout(lib, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "jat_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(jat_gemm_epilogue), offsetof(jat_gemm_epilogue, gate),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(jat_gemm_epilogue),'
+        ' offsetof(jat_gemm_epilogue, gate),'
         ' offsetof(jat_gemm_epilogue, t_out), sizeof(jat_dit_weights), offsetof(jat_dit_weights, pe_w1),'
-        ' offsetof(jat_dit_weights, rope_sin), sizeof(jat_dit_workspace), offsetof(jat_dit_workspace, block_out));return 0;}\n')
+        ' offsetof(jat_dit_weights, rope_sin), sizeof(jat_dit_workspace), offsetof(jat_dit_workspace, block_out),'
+        ' offsetof(jat_gemm_epilogue, drop_seed), offsetof(jat_gemm_epilogue, gate_rowscale), sizeof(jat_dit_saved),'
+        ' offsetof(jat_dit_saved, seed), offsetof(jat_dit_saved, dp_scale), sizeof(jat_dit_bwd_scratch));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    E, W, S = lib.GemmEpilogue, lib.DitWeights, lib.DitWorkspace
+    E, W, S, V = lib.GemmEpilogue, lib.DitWeights, lib.DitWorkspace, lib.DitSaved
     want = [ctypes.sizeof(E), E.gate.offset, E.t_out.offset, ctypes.sizeof(W), W.pe_w1.offset, W.rope_sin.offset,
-            ctypes.sizeof(S), S.block_out.offset]
+            ctypes.sizeof(S), S.block_out.offset, E.drop_seed.offset, E.gate_rowscale.offset, ctypes.sizeof(V),
+            V.seed.offset, V.dp_scale.offset, ctypes.sizeof(lib.DitBwdScratch)]
     assert got == want
 
 

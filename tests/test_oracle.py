@@ -122,3 +122,72 @@ def test_oracle_sampler_matches_reference_sampler():
                                  num_q_heads=4, num_kv_heads=2)
     assert np.abs(got - want).max() < 1e-4
     assert rel_l2(got, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# tests/_torch_dit.py (the differentiable restatement used by the train-mode dropout parity tests on the GPU) pinned
+# against the unmodified reference: eval mode, and TRAIN mode with the reference's nn.Dropout / drop_path draws replaced
+# by given masks -- which pins where each mask enters the computation (jat_audiosr_v2.py:158,250,252,281,287).
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not have_reference(), reason="reference not mounted")
+@pytest.mark.parametrize("cls_idx,rms", [(0, False), (1, True)])
+def test_torch_restatement_with_masks_matches_reference(cls_idx, rms):
+    import torch
+    from tests._torch_dit import dit_forward
+    ref_cls = import_reference()[cls_idx]
+    cfg = dict(input_channels=16, cond_channels=16, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
+               bottleneck_dim=64, mlp_ratio=2.0, dropout=0.25, drop_path_rate=0.5)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = rerandomise_zero_init(ref_cls(**cfg), bf16_exact=False)
+    B, T = 3, 30
+    N, D, F_ = 8, 128, 256
+    g = torch.Generator().manual_seed(5)
+    x_t, cond = torch.randn(B, 16, T, generator=g), torch.randn(B, 16, T, generator=g)
+    t = torch.rand(B, generator=g)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.eval()
+    with torch.no_grad():
+        want = model(x_t, t, cond)
+        got = dit_forward(sd, cfg, x_t, t, cond, rms=rms)
+    assert rel_l2(got.numpy(), want.numpy()) < 1e-5
+
+    def bern(shape, p):
+        return (torch.rand(shape, generator=g) >= p).float() / (1 - p)
+    masks = {"attn": [bern((B, 2, N, N), 0.25) for _ in range(2)], "hid": [bern((B * N, F_), 0.25) for _ in range(2)],
+             "out": [bern((B * N, D), 0.25) for _ in range(2)], "path": bern((2, 2, B), 0.5)}
+
+    class Mask(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            return x * self.m.view(x.shape)
+
+    class PathMask(torch.nn.Module):  # called twice per block forward: attention branch, then MLP branch
+        def __init__(self, ms):
+            super().__init__()
+            self.ms, self.n = ms, 0
+
+        def forward(self, x):
+            m = self.ms[self.n % 2]
+            self.n += 1
+            return x * m[:, None, None]
+    mod = sys.modules[ref_cls.__module__]
+    for i, blk in enumerate(model.blocks):
+        blk.attn.dropout = Mask(masks["attn"][i])
+        blk.mlp[2] = Mask(masks["hid"][i])
+        blk.mlp[4] = Mask(masks["out"][i])
+        blk.drop_path = PathMask([masks["path"][i, 0], masks["path"][i, 1]])
+    assert hasattr(mod, "drop_path")
+    model.train()
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "rope" not in k) for k, v in sd.items()}
+    got = dit_forward(params, cfg, x_t, t, cond, rms=rms, masks=masks)
+    want = model(x_t, t, cond)
+    assert rel_l2(got.detach().numpy(), want.detach().numpy()) < 1e-5
+    hr = torch.randn(B, 16, T, generator=g)
+    torch.nn.functional.mse_loss(got, hr).backward()
+    torch.nn.functional.mse_loss(want, hr).backward()
+    for k, prm in model.named_parameters():
+        assert rel_l2(params[k].grad.numpy(), prm.grad.numpy()) < 2e-4, k
