@@ -40,7 +40,8 @@ typedef struct jat_ctx jat_ctx; /* opaque: device id, SM count, TMA descriptor c
 
 int jat_abi_version(void);
 const char* jat_last_error(void);
-/* Binds to CUDA device `device`, resolves the driver entry points; no device memory is allocated. */
+/* Binds to CUDA device `device`, resolves the driver entry points and allocates the library's only device memory: a
+ * fixed ~19 MB scratch for the GEMM tail split (below).  Calls on one ctx must be issued to one stream at a time. */
 int jat_create(int device, jat_ctx** out);
 void jat_destroy(jat_ctx* ctx);
 int jat_sm_count(const jat_ctx* ctx);
@@ -332,6 +333,10 @@ int64_t jat_launch_count(const jat_ctx* ctx);
 
 /* Default GEMM tile configuration used when a call passes cta_pair < 0 / block_n == 0. */
 int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
+/* Tail split (default off): when the persistent tile schedule ends in a partial wave, the tiles of that wave are cut
+ * along K into parts that fill the machine; the parts park their f32 accumulators in the ctx scratch and the part that
+ * arrives last sums them IN PART ORDER and runs the fused epilogue, so results stay bit-reproducible run to run. */
+int jat_set_gemm_tail_split(jat_ctx* ctx, int enable);
 
 /* Per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline of
  * each kernel class inside a real step).  Between begin and end every launch is bracketed by an event
@@ -398,6 +403,10 @@ int jat_crossfade_denorm(jat_ctx* ctx, const float* chunks, int n_chunks, int C,
 /* Debug aid: when `buf` (DEVICE, 128 x int64) is non-NULL, CTA (0,0,0) of every following attention launch
  * stores clock64() timestamps of its pipeline events there (scripts/att_trace.py decodes them). NULL = off. */
 int jat_debug_set_attention_trace(jat_ctx* ctx, void* buf);
+/* The same for the GEMM kernel: 64 work items x 8 slots of int64 (CTA 0): 0 producer starts the item, 1/2 MMA issuer
+ * before/after the accumulator-stage wait, 3 MMA issuer committed the item, 4/5 epilogue warp before/after the
+ * accumulator-full wait, 6 epilogue done. */
+int jat_debug_set_gemm_trace(jat_ctx* ctx, void* buf);
 
 #ifdef __cplusplus
 }

@@ -121,7 +121,9 @@ SIGNATURES = {
     "jat_sm_count": (_i, [_vp]),
     "jat_launch_count": (_i64, [_vp]),
     "jat_set_gemm_config": (_i, [_vp, _i, _i]),
+    "jat_set_gemm_tail_split": (_i, [_vp, _i]),
     "jat_debug_set_attention_trace": (_i, [_vp, _vp]),
+    "jat_debug_set_gemm_trace": (_i, [_vp, _vp]),
     "jat_profile_begin": (_i, [_vp]),
     "jat_profile_end": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "jat_adaln_norm_modulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _i, _i, _i, _vp]),

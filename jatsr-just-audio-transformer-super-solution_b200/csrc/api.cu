@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -39,7 +40,13 @@ struct jat_ctx {
     size_t ev_used;
     cudaStream_t cur_stream;
     long long* att_trace;  // debug: device buffer of 128 clock64 slots for the attention kernel, or NULL
+    // GEMM tail split (see GemmParams): partial-accumulator workspace (one 128x256 f32 tile per SM) + arrival counters
+    float* tail_ws;
+    int* tail_cnt;
+    int tail_split;        // 1 = cut the tiles of a partial last wave along K
+    long long* gemm_trace; // debug: device buffer of 64 x 8 clock64 slots for the GEMM kernel, or NULL
 };
+static const size_t kTailWsBytesPerSM = 128 * 256 * sizeof(float);
 
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
@@ -101,11 +108,25 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->ev_used = 0;
     c->cur_stream = nullptr;
     c->att_trace = nullptr;
+    c->tail_ws = nullptr;
+    c->tail_cnt = nullptr;
+    c->tail_split = 0;
+    c->gemm_trace = nullptr;
+    const size_t cnt_bytes = (size_t)c->sm_count * GEMM_EPI_WARPS * sizeof(int);
+    if (cudaMalloc(&c->tail_ws, kTailWsBytesPerSM * c->sm_count) != cudaSuccess ||
+        cudaMalloc(&c->tail_cnt, cnt_bytes) != cudaSuccess || cudaMemset(c->tail_cnt, 0, cnt_bytes) != cudaSuccess) {
+        cudaFree(c->tail_ws);
+        cudaFree(c->tail_cnt);
+        delete c;
+        return cuda_fail(cudaGetLastError(), "jat_create: GEMM tail-split workspace");
+    }
     *out = c;
     return 0;
 }
 extern "C" void jat_destroy(jat_ctx* ctx) {
     if (!ctx) return;
+    cudaFree(ctx->tail_ws);
+    cudaFree(ctx->tail_cnt);
     for (cudaEvent_t e : ctx->ev_start) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_stop) cudaEventDestroy(e);
     delete ctx;
@@ -117,6 +138,18 @@ extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
     if (block_n != 0 && block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "block_n must be 0/128/256");
     ctx->gemm_cta_pair = cta_pair ? 1 : 0;
     ctx->gemm_block_n = block_n;
+    return 0;
+}
+
+extern "C" int jat_debug_set_gemm_trace(jat_ctx* ctx, void* buf) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    ctx->gemm_trace = (long long*)buf;
+    return 0;
+}
+
+extern "C" int jat_set_gemm_tail_split(jat_ctx* ctx, int enable) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    ctx->tail_split = enable ? 1 : 0;
     return 0;
 }
 
@@ -253,7 +286,8 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
         configured = true;
     }
     int clusters = ctx->sm_count / CG;
-    if (clusters > p.num_tiles * p.k_splits) clusters = p.num_tiles * p.k_splits;
+    const int num_work = p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
+    if (clusters > num_work) clusters = num_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -362,6 +396,27 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     if (p.k_splits > 1 && e->kind != JAT_EPI_GATE_RESIDUAL && e->kind != JAT_EPI_ACCUM)
         return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: k_splits needs a reduce-add epilogue (GATE_RESIDUAL / ACCUM)");
     if (p.k_splits > p.num_k_blocks) p.k_splits = p.num_k_blocks;
+    // Tail split: when the last wave of the persistent schedule is partial, its tiles are cut along K so that the
+    // wave fills the machine (e.g. out_proj / fc2: 380 tiles on 74 CTA pairs = 5 waves + 10 tiles -> 10 x 7 parts).
+    {
+        static const int dbg = getenv("JAT_DBG_GEMM_SKIP") ? atoi(getenv("JAT_DBG_GEMM_SKIP")) : 0;
+        p.dbg_skip = dbg;
+        p.trace = ctx->gemm_trace;
+    }
+    p.head_tiles = p.num_tiles;
+    p.tail_splits = 1;
+    p.tail_ws = ctx->tail_ws;
+    p.tail_cnt = ctx->tail_cnt;
+    {
+        const int clusters = ctx->sm_count / cg;
+        const int rem = p.num_tiles % clusters;
+        if (ctx->tail_split && p.k_splits == 1 && p.num_tiles > clusters && rem > 0) {
+            int splits = clusters / rem;
+            if (splits > 8) splits = 8;
+            if (splits > p.num_k_blocks / 2) splits = p.num_k_blocks / 2;
+            if (splits >= 2) { p.head_tiles = p.num_tiles - rem; p.tail_splits = splits; }
+        }
+    }
 
     switch (e->kind) {
         case JAT_EPI_BIAS_ACT:

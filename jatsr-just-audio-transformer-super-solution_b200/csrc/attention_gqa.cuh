@@ -110,7 +110,9 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     uint64_t* bar_o_free = bars + 13;   // O_A / O_B read out by the 128 epilogue threads
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (warp-uniform values go through a full-mask shuffle so that the compiler keeps the MMA issue paths on the
+    //  uniform datapath -- see elect_one())
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int q_row0 = b * p.N + qt * ATT_BQ;  // global token row of this tile's first query
     const int kv_row0 = b * p.N;
@@ -154,24 +156,30 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp >= 12) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // descriptors as (lo, hi) 32-bit halves: hi is the same layout constant for every operand
         const uint32_t desc_hi = (uint32_t)(umma_smem_desc_sw128(0) >> 32);
-        if (warp == 12 && lane == 0) {
+        if (warp == 12) {
             // -------------------------------------------------------------- S MMA issue
+            // The whole warp runs the (uniform) control flow; one elected lane issues.  Under elect.sync the operands stay
+            // in uniform registers, so the MMAs of a chain issue back to back (under `lane == 0` every tcgen05.mma was
+            // wrapped in an R2UR waterfall that cost more than the MMA itself for these short N = 64 / 176 shapes).
             constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, NKH);
             const uint32_t q_lo0 = (uint32_t)umma_smem_desc_sw128(smem_u32(sQ));
             const uint32_t k_lo0 = (uint32_t)umma_smem_desc_sw128(smem_u32(sK));
             auto issue_s = [&](int h, int half) {  // S_half(h) = Q(h) K_half^T into the shared S region
-                const uint32_t q_lo = launder_u32(q_lo0 + (uint32_t)((h & 1) * (ATT_Q_BYTES >> 4)));
-                const uint32_t k_lo = launder_u32(k_lo0 + (uint32_t)(half * ((NKH * 128) >> 4)));
+                const uint32_t q_lo = q_lo0 + (uint32_t)((h & 1) * (ATT_Q_BYTES >> 4));
+                const uint32_t k_lo = k_lo0 + (uint32_t)(half * ((NKH * 128) >> 4));
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < ATT_HD / 16; ++k)
-                    umma_bf16_ss_lohi(tmem_base, q_lo + 2 * k, desc_hi, k_lo + 2 * k, desc_hi, idesc_s, (uint32_t)(k != 0));
-                umma_commit(&bar_s_full[half]);
+                    for (int k = 0; k < ATT_HD / 16; ++k)
+                        umma_bf16_ss_lohi(tmem_base, q_lo + 2 * k, desc_hi, k_lo + 2 * k, desc_hi, idesc_s, (uint32_t)(k != 0));
+                    umma_commit(&bar_s_full[half]);
+                }
+                __syncwarp();
             };
             mbar_wait_backoff(bar_k, 0);
             mbar_wait_backoff(&bar_q[0], 0);
@@ -183,30 +191,34 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 mbar_wait_backoff(&bar_s_free[0], ph);  // S_A(h) is in registers -> the S region is free
                 tc_fence_after();
                 issue_s(h, 1);
-                ATT_TRACE(4 * h + 0);
+                if (lane == 0) ATT_TRACE(4 * h + 0);
                 if (h + 1 < p.G) {
                     mbar_wait_backoff(&bar_q[(h + 1) & 1], (uint32_t)(((h + 1) >> 1) & 1));
                     mbar_wait_backoff(&bar_s_free[1], ph);  // S_B(h) is in registers
                     tc_fence_after();
                     issue_s(h + 1, 0);
-                    ATT_TRACE(4 * h + 1);
+                    if (lane == 0) ATT_TRACE(4 * h + 1);
                 }
             }
-        } else if (warp == 13 && lane == 0) {
+        } else if (warp == 13) {
             // -------------------------------------------------------------- P.V MMA issue
             constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_HD, /*a_major=*/0, /*b_major=*/1);
             const uint32_t v_lo0 = (uint32_t)umma_smem_desc_sw128(smem_u32(sV));
-            auto issue_pv = [&](int half) {  // O_half = P_half V_half
+            auto issue_pv = [&](int half, bool last) {  // O_half = P_half V_half
                 const uint32_t d = tmem_base + (uint32_t)(half ? ATT_OB_COL : ATT_OA_COL);
                 // A: P_half in TMEM, 8 packed columns per 16-key step;
                 // B: V rows [16 ks, 16 ks + 16): MN-major, 2 groups of 8 key rows (+2 KB per step)
-                const uint32_t a = launder_u32(tmem_base + (uint32_t)(Cfg::P_COL + half * (NKH / 2)));
-                const uint32_t v_lo = launder_u32(v_lo0 + (uint32_t)(half * (NKH / 16) * (2048 >> 4)));
+                const uint32_t a = tmem_base + (uint32_t)(Cfg::P_COL + half * (NKH / 2));
+                const uint32_t v_lo = v_lo0 + (uint32_t)(half * (NKH / 16) * (2048 >> 4));
+                if (elect_one()) {
 #pragma unroll
-                for (int i = 0; i < NKH / 16; ++i)
-                    umma_bf16_ts_lohi(d, a + (uint32_t)(i * 8), v_lo + (uint32_t)(i * (2048 >> 4)), desc_hi, idesc_pv,
-                                      (uint32_t)(i != 0));
-                umma_commit(&bar_p_free[half]);
+                    for (int i = 0; i < NKH / 16; ++i)
+                        umma_bf16_ts_lohi(d, a + (uint32_t)(i * 8), v_lo + (uint32_t)(i * (2048 >> 4)), desc_hi, idesc_pv,
+                                          (uint32_t)(i != 0));
+                    umma_commit(&bar_p_free[half]);
+                    if (last) umma_commit(bar_o_full);
+                }
+                __syncwarp();
             };
             mbar_wait_backoff(bar_v, 0);
 #pragma unroll 1
@@ -215,13 +227,12 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 if (h > 0) mbar_wait_backoff(bar_o_free, (uint32_t)((h - 1) & 1));  // O(h-1) has left TMEM
                 mbar_wait_backoff(&bar_p_full[0], ph);
                 tc_fence_after();
-                issue_pv(0);
-                ATT_TRACE(4 * h + 2);
+                issue_pv(0, false);
+                if (lane == 0) ATT_TRACE(4 * h + 2);
                 mbar_wait_backoff(&bar_p_full[1], ph);
                 tc_fence_after();
-                issue_pv(1);
-                umma_commit(bar_o_full);
-                ATT_TRACE(4 * h + 3);
+                issue_pv(1, true);
+                if (lane == 0) ATT_TRACE(4 * h + 3);
             }
         } else if (warp == 14 && lane == 0) {
             // Q(h+2) into stage (h & 1) once S_B(h), the last reader of that stage, has retired

@@ -48,7 +48,66 @@ struct GemmParams {
                              // on acc + bias before the gate; DACT: the same mask applied to the incoming gradient)
     const void* aux;         // EPI_DACT: pre-activation u bf16 [M, ld_aux];  EPI_BIAS_ACT: optional bf16 copy of (acc + bias)
     long long ld_aux;
+    // Tail split (deterministic stream-K fix-up for the last, partial wave): tiles [0, head_tiles) are whole work items
+    // (x k_splits); each tile in [head_tiles, num_tiles) is cut into tail_splits reduction parts whose f32 partial
+    // accumulators go to tail_ws; the part that arrives last (tail_cnt) sums them in part order and runs the epilogue.
+    int head_tiles, tail_splits;
+    float* tail_ws;
+    int* tail_cnt;
+    long long* trace;  // diagnostics: clock64 timestamps of cluster 0 / CTA rank 0, 8 slots per work item, or NULL
+    int dbg_skip;  // diagnostics only (JAT_DBG_GEMM_SKIP): bit 0 = do not load A, bit 1 = do not load B (results are garbage)
 };
+
+#define GEMM_TRACE(item, slot)                                                                      \
+    do {                                                                                            \
+        if (p.trace != nullptr && blockIdx.x == 0 && (item) < 64) p.trace[(item) * 8 + (slot)] = clock64(); \
+    } while (0)
+
+struct GemmWork {
+    int tile, kb0, kb1, part, tail;  // tail = index of the split tail tile, or -1
+};
+__device__ __forceinline__ int gemm_num_work(const GemmParams& p) {
+    return p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
+}
+__device__ __forceinline__ GemmWork gemm_decode_work(const GemmParams& p, int work) {
+    GemmWork w;
+    int parts;
+    const int head_items = p.head_tiles * p.k_splits;
+    if (work < head_items) {
+        w.tile = work / p.k_splits; w.part = work - w.tile * p.k_splits; parts = p.k_splits; w.tail = -1;
+    } else {
+        const int w2 = work - head_items;
+        const int t2 = w2 / p.tail_splits;
+        w.tile = p.head_tiles + t2; w.part = w2 - t2 * p.tail_splits; parts = p.tail_splits;
+        w.tail = p.tail_splits > 1 ? t2 : -1;
+    }
+    w.kb0 = (int)((long long)p.num_k_blocks * w.part / parts);
+    w.kb1 = (int)((long long)p.num_k_blocks * (w.part + 1) / parts);
+    return w;
+}
+
+// Sum of the `parts` partial accumulators of a split tail tile, columns [col, col + 4*NV) of this thread's row, in
+// part order (deterministic).  Workspace region layout: float4 unit u = col/4 of lane l at [(u * 32 + l)].
+template <int NV>
+__device__ __forceinline__ void gemm_ws_sum(const float* region0, long long part_stride, int parts, int col, int lane,
+                                            uint32_t* v) {
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < parts; ++q) {
+        const float4* src = reinterpret_cast<const float4*>(region0 + q * part_stride) + (col >> 2) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 t = __ldcg(src + i * 32);
+            acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[4 * i + 0] = __float_as_uint(acc[i].x); v[4 * i + 1] = __float_as_uint(acc[i].y);
+        v[4 * i + 2] = __float_as_uint(acc[i].z); v[4 * i + 3] = __float_as_uint(acc[i].w);
+    }
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -132,9 +191,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* bar_tmem_empty = bar_tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    // warp-uniform values are passed through a full-mask shuffle: that is what tells the compiler they are uniform, so
+    // that the MMA / TMA issue paths keep descriptors and addresses in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = (CG == 2) ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
     const int cluster_id = blockIdx.x / CG;
     const int num_clusters = gridDim.x / CG;
 
@@ -161,25 +222,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int num_work = p.num_tiles * p.k_splits;
+            const int num_work = gemm_num_work(p);
             for (int work = cluster_id; work < num_work; work += num_clusters) {
-                const int tile = work / p.k_splits, part = work - tile * p.k_splits;
-                const int kb0 = (int)((long long)p.num_k_blocks * part / p.k_splits);
-                const int kb1 = (int)((long long)p.num_k_blocks * (part + 1) / p.k_splits);
+                const GemmWork wk = gemm_decode_work(p, work);
+                const int tile = wk.tile, kb0 = wk.kb0, kb1 = wk.kb1;
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
                 const int a_row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM;
                 const int b_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
+                GEMM_TRACE(work / num_clusters, 0);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (p.dbg_skip != 0) {  // bandwidth diagnostics: stream only one (or neither) operand
+                        const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : (uint32_t)Cfg::A_BYTES) + ((p.dbg_skip & 2) ? 0u : (uint32_t)Cfg::B_BYTES);
+                        if (bytes == 0) { if (CG == 1 || cta_rank == 0) mbar_arrive(&bar_full[stage]); }
+                        else if (CG == 1) mbar_expect_tx(&bar_full[stage], bytes);
+                        else if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], bytes * 2);
+                        if (!(p.dbg_skip & 1)) tma_load_tile<CG>(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
+                        if (!(p.dbg_skip & 2)) tma_load_tile<CG>(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (CG == 1) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
                     else if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES * 2);  // both CTAs' bytes
                     if constexpr (A_MN) {  // boxes of 64 reduction rows x 64 output rows (8 KB each)
@@ -202,54 +273,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();  // reconverge before the (warp-aligned) teardown barrier
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------------ MMA issuer (lane 0 issues; warp-uniform control)
+        // The tensor pipe has next to no queue: a tcgen05.mma issues only when the previous one is nearly done (issue cost
+        // ~= execution time, scripts/microbench_sm100.cu), so every instruction between two MMAs is a pipe bubble.  The
+        // path between the last MMA of a tile and the first of the next is therefore kept minimal: no work decoding
+        // (items of a launch without split-K all span the same k-blocks), and the next tile's accumulator-stage wait
+        // comes right after the commit, before the loop overhead.
         if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, A_MN, B_MN);
             // per 16-element k-step: +32 B inside the 128B swizzle atom (K-major) or +16 rows x 128 B (MN-major)
             constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : 2u, b_kstep = B_MN ? (2048u >> 4) : 2u;
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;
-            uint32_t aphase = 0;
-            const int num_work = p.num_tiles * p.k_splits;
+            const int num_work = gemm_num_work(p);
+            const bool uniform = p.k_splits == 1 && p.tail_splits == 1;  // every item spans all k-blocks
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
             for (int work = cluster_id; work < num_work; work += num_clusters) {
-                const int tile = work / p.k_splits, part = work - tile * p.k_splits;
-                const int kb0 = (int)((long long)p.num_k_blocks * part / p.k_splits);
-                const int kb1 = (int)((long long)p.num_k_blocks * (part + 1) / p.k_splits);
+                int nkb = p.num_k_blocks;
+                if (!uniform) { const GemmWork wk = gemm_decode_work(p, work); nkb = wk.kb1 - wk.kb0; }
                 mbar_wait(&bar_tmem_empty[as], aphase ^ 1);
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                if (lane == 0) GEMM_TRACE(work / num_clusters, 2);
+                for (int i = 0; i < nkb; ++i) {
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint64_t a_desc = A_MN ? umma_smem_desc_sw128_mn(sa, 8192) : umma_smem_desc_sw128(sa);
                         const uint64_t b_desc = B_MN ? umma_smem_desc_sw128_mn(sa + Cfg::A_BYTES, 8192)
                                                      : umma_smem_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / 16; ++k)
-                            umma_bf16_ss<CG>(d_tmem, a_desc + a_kstep * k, b_desc + b_kstep * k, idesc,
-                                             (uint32_t)((kb != kb0) | (k != 0)));
+                            umma_bf16_ss<CG>(d_tmem, a_desc + a_kstep * k, b_desc + b_kstep * k, idesc, (uint32_t)((i | k) != 0));
                         if constexpr (CG == 1) umma_commit(&bar_empty[stage]);
                         else umma_commit_2sm(&bar_empty[stage], 0x3);
+                        if (i + 1 == nkb) {
+                            if constexpr (CG == 1) umma_commit(&bar_tmem_full[as]);
+                            else umma_commit_2sm(&bar_tmem_full[as], 0x3);
+                            GEMM_TRACE(work / num_clusters, 3);
+                        }
                     }
-                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (lane == 0) {
-                    if constexpr (CG == 1) umma_commit(&bar_tmem_full[as]);
-                    else umma_commit_2sm(&bar_tmem_full[as], 0x3);
-                }
-                __syncwarp();
                 if ((as ^= 1) == 0) aphase ^= 1;
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
         const int quad = warp & 3;       // TMEM lane quadrant this warp may access
         const int wg = (warp - 4) >> 2;  // column half
-        const int row_in_tile = quad * 32 + lane;
         constexpr int HALF = BN / 2;
         uint8_t* my_stage = staging + (warp - 4) * 2 * GEMM_SLAB_BYTES;
         const uint32_t slab_row[2] = {smem_u32(my_stage) + (uint32_t)lane * 128u,
@@ -257,18 +329,67 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
-        const int num_work = p.num_tiles * p.k_splits;
+        const int num_work = gemm_num_work(p);
+        constexpr long long WS_REGION = 32LL * HALF;                         // floats per (part, CTA, warp) region
+        constexpr long long WS_PART_STRIDE = (long long)CG * GEMM_EPI_WARPS * WS_REGION;
         for (int work = cluster_id; work < num_work; work += num_clusters) {
-            const int tile = work / p.k_splits, part = work - tile * p.k_splits;
-            const bool add_bias = p.bias != nullptr && part == 0;  // split-K: the bias goes in with the first partial sum
+            const GemmWork wk = gemm_decode_work(p, work);
+            const int tile = wk.tile;
+            // split-K (reduce-add epilogues): the bias goes in with the first partial sum; tail split: with the fix-up
+            const bool add_bias = p.bias != nullptr && (wk.part == 0 || wk.tail >= 0);
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
             const int row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM + quad * 32;  // first row of this warp's slab
             const int m = row0 + lane;
             const bool row_ok = m < p.M;
             const int n_base = n_blk * BN + wg * HALF;
+            if (warp == 4 && lane == 0) GEMM_TRACE(work / num_clusters, 4);
             mbar_wait(&bar_tmem_full[as], aphase);
             tc_fence_after();
+            if (warp == 4 && lane == 0) GEMM_TRACE(work / num_clusters, 5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + wg * HALF);
+            // ---- split tail tile: park this part's accumulator in the workspace; only the warp that arrives last
+            //      (per tile, CTA, warp slab) goes on to the epilogue, on the in-order sum of all parts
+            const float* ws_region = nullptr;
+            if (wk.tail >= 0) {
+                const long long slab = ((long long)cta_rank * GEMM_EPI_WARPS + (warp - 4)) * WS_REGION;
+                float* tile_ws = p.tail_ws + (long long)wk.tail * p.tail_splits * WS_PART_STRIDE + slab;
+                float4* dst = reinterpret_cast<float4*>(tile_ws + wk.part * WS_PART_STRIDE) + lane;
+#pragma unroll 1
+                for (int c = 0; c < HALF / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        __stcg(dst + (c * 8 + i) * 32, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                }
+                tc_fence_before();
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
+                    else mbar_arrive_cluster(&bar_tmem_empty[as], 0);
+                    int* cnt = p.tail_cnt + (wk.tail * CG + (int)cta_rank) * GEMM_EPI_WARPS + (warp - 4);
+                    last = atomicAdd(cnt, 1) == p.tail_splits - 1;
+                    if (last) *cnt = 0;  // every part has arrived: reset for the next launch
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if ((as ^= 1) == 0) aphase ^= 1;
+                if (!last) continue;
+                __threadfence();
+                ws_region = tile_ws;
+            }
+            // accumulator columns [col, col+32) / [col, col+16) of this thread's row: from TMEM, or the summed partials
+            auto load32 = [&](int col, uint32_t (&v)[32]) {
+                if (ws_region == nullptr) { tmem_ld_32x32(taddr + col, v); tmem_ld_wait(); }
+                else gemm_ws_sum<8>(ws_region, WS_PART_STRIDE, p.tail_splits, col, lane, v);
+            };
+            auto load16 = [&](int col, uint32_t (&v)[16]) {
+                if (ws_region == nullptr) tmem_ld_32x16(taddr + col, v);
+                else gemm_ws_sum<4>(ws_region, WS_PART_STRIDE, p.tail_splits, col, lane, v);
+            };
 
             if constexpr ((EPI == EPI_BIAS_ACT && OUT_BF16) || EPI == EPI_DACT) {
                 // BIAS_ACT: out = act(acc + bias)  [+ optional bf16 copy of the pre-activation acc + bias to p.aux,
@@ -285,8 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int hx = 0; hx < 2; ++hx) {
                         uint32_t v[32];
-                        tmem_ld_32x32(taddr + sl * 64 + hx * 32, v);
-                        tmem_ld_wait();
+                        load32(sl * 64 + hx * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             float f[8];
@@ -352,8 +472,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr + sl * 32, v);
-                    tmem_ld_wait();
+                    load32(sl * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
@@ -406,8 +525,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
                         uint32_t lo[16], hi[16];
-                        tmem_ld_32x16(taddr + hh * 64 + s * 16, lo);
-                        tmem_ld_32x16(taddr + hh * 64 + 32 + s * 16, hi);
+                        load16(hh * 64 + s * 16, lo);
+                        load16(hh * 64 + 32 + s * 16, hi);
                         tmem_ld_wait();
                         float ol[16], oh[16];
 #pragma unroll
@@ -453,14 +572,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
                 for (int c = 0; c < HALF / 32; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr + c * 32, v);
-                    tmem_ld_wait();
+                    load32(c * 32, v);
                     const int n0 = n_base + c * 32;
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                             const float r0 = __uint_as_float(v[j + 0]) + b4.x, r1 = __uint_as_float(v[j + 1]) + b4.y,
                                         r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
                             float* o = obase + (long long)((n0 + j) >> 2) * p.t_out;
@@ -478,9 +596,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
 
+            if (wk.tail >= 0) continue;  // a split tail tile handed its accumulator stage back right after parking it
             // all TMEM reads of this accumulator stage are done -> hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
+            if (warp == 4 && lane == 0) GEMM_TRACE(work / num_clusters, 6);
             if (lane == 0) {
                 if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
                 else mbar_arrive_cluster(&bar_tmem_empty[as], 0);

@@ -105,6 +105,13 @@ def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, b
     return out
 
 
+def set_gemm_tail_split(device, enable):
+    """Toggle the GEMM tail split (deterministic split-K fix-up of a partial last wave) on a device's context."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    L.check(L.load().jat_set_gemm_tail_split(L.context(idx), int(bool(enable))))
+
+
 def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None, drop_p=0.0, drop_seed=0):
     """lse: optional f32 [B, Hq, N] output (log2-domain log-sum-exp per query row, for the backward pass).
     drop_p / drop_seed: train-mode dropout on the probabilities (mask row = (b*Hq + h)*N + query, col = key)."""

@@ -239,6 +239,67 @@ def test_gemm_rejects_bad_shapes(ops, L):
         ops.gemm(A, W)
 
 
+# ------------------------------------------------------------------------------------------- GEMM tail split
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("kind", ["bias_f32", "bias_gelu_bf16", "qkv_rope", "gate_residual", "unpatchify", "dgrad_dact"])
+def test_gemm_tail_split_matches_unsplit_and_is_deterministic(ops, L, cta_pair, block_n, kind):
+    """Headline-sized problems whose persistent schedule ends in a partial wave: the tiles of that wave are cut along K
+    and fixed up in part order (jat_set_gemm_tail_split).  Same result as the unsplit schedule up to f32 summation
+    order, bit-identical run to run, and correct against torch on the rows of the split tiles (the last M blocks)."""
+    B, Ntok = 56, 345
+    M = B * Ntok
+    shapes = {"bias_f32": (1280, 512), "bias_gelu_bf16": (512, 1280), "qkv_rope": (1792, 1280), "gate_residual": (1280, 1280),
+              "unpatchify": (4096, 256), "dgrad_dact": (1280, 512)}
+    N, K = shapes[kind]
+    A, W, bias = _ab(M, N, K, seed=11)
+    cos, sin = (t.to(dev()) for t in _rope_tables())
+    gate = torch.randn(B, N, device=dev())
+    x0 = torch.randn(M, N, device=dev())
+    u = torch.randn(M, N, device=dev()).to(torch.bfloat16)
+    Wt = W.t().contiguous()  # [K, N] for the dgrad case: dX[M, N] = dY[M, K] Wt[K, N]
+
+    def run():
+        if kind == "bias_f32":
+            return ops.gemm(A, W, bias=bias, out_dtype=L.DTYPE_F32, cta_pair=cta_pair, block_n=block_n)
+        if kind == "bias_gelu_bf16":
+            return ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, cta_pair=cta_pair, block_n=block_n)
+        if kind == "qkv_rope":
+            return ops.gemm(A, W, kind=L.EPI_QKV_ROPE, tokens_per_batch=Ntok, rope_cos=cos, rope_sin=sin, rope_cols=1536,
+                            cta_pair=cta_pair, block_n=block_n)
+        if kind == "gate_residual":
+            x = x0.clone()
+            ops.gemm(A, W, kind=L.EPI_GATE_RESIDUAL, out=x, bias=bias, gate=gate, gate_batch_stride=N,
+                     tokens_per_batch=Ntok, cta_pair=cta_pair, block_n=block_n)
+            return x
+        if kind == "unpatchify":
+            out = torch.empty(B, N // 4, 1378, device=dev())
+            ops.gemm(A, W, kind=L.EPI_UNPATCHIFY, out=out, bias=bias, tokens_per_batch=Ntok, patch_len=4, t_out=1378,
+                     cta_pair=cta_pair, block_n=block_n)
+            return out
+        return ops.gemm(A, Wt, kind=L.EPI_DACT, act=L.ACT_GELU_ERF, aux=u, w_transposed=True, cta_pair=cta_pair,
+                        block_n=block_n)
+    try:
+        ops.set_gemm_tail_split(dev(), False)
+        plain = run()
+        ops.set_gemm_tail_split(dev(), True)
+        split = run()
+        again = run()
+    finally:
+        ops.set_gemm_tail_split(dev(), False)  # the library default
+    assert torch.equal(split, again)
+    if split.dtype == torch.bfloat16:
+        # one bf16 ulp where the f32 sums straddle a rounding boundary
+        assert (split.float() - plain.float()).abs().max() <= 2 ** -7 * plain.float().abs().max()
+        assert rel_l2(split.float(), plain.float()) < 1e-3
+    else:
+        assert rel_l2(split, plain) < 2e-6
+    if kind == "gate_residual":  # against torch on the last rows (split tiles live in the last M blocks)
+        lo = M - 700
+        y = A[lo:].float() @ W.float().t() + bias
+        want = x0[lo:] + gate.repeat_interleave(Ntok, 0)[lo:] * y
+        assert rel_l2(split[lo:], want) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 16, 4), (2, 256, 4, 4), (1, 352, 5, 1)])
 def test_gqa_attention(ops, B, N, Hq, Hkv):
