@@ -309,7 +309,8 @@ def train_main(a, K, W, rank, world, local):
         dist.init_process_group("nccl", init_method="env://")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cfg = dict(CFG, dropout=0.0, drop_path_rate=0.0)
+    cfg = dict(CFG)  # dropout 0.1, drop_path 0.05: the reference's training configuration (train_ddp_v3mod2.py:343-355)
+    from jat_b200 import training
     cls = jat_b200.JaT_AudioSR_V2 if a.norm == "layernorm" else jat_b200.JaT_AudioSR_V3
     torch.manual_seed(0)
     with torch.device(dev):
@@ -325,16 +326,21 @@ def train_main(a, K, W, rank, world, local):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.1, fused=True)   # train_ddp_v3mod2.py:709
     gd = torch.Generator(device=dev).manual_seed(100 + rank)
-    hr = torch.randn(B, C, T, generator=gd, device=dev)
-    lr = torch.randn(B, C, T, generator=gd, device=dev)
+    hr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3                   # raw (un-normalised) DAC latents
+    lr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3
+    hr_mean = torch.full((1, C, 1), 0.3, device=dev)
+    hr_std = torch.full((1, C, 1), 2.0, device=dev)
 
     def step():
         u = torch.rand(B, generator=gd, device=dev)                                   # U-shaped t, :449-457
         t = torch.where(u < 0.5, (2 * u).sqrt() / 2, 1 - (2 * (1 - u)).sqrt() / 2)
         noise = torch.randn(B, C, T, generator=gd, device=dev)
-        z_t = t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * noise                    # :881-883
+        cond_noise = torch.randn(B, C, T, generator=gd, device=dev)
+        # normalise + 5 % conditional noise + z_t = t x + (1 - t) eps in one kernel (:856-883)
+        hr_norm, lr_cond, z_t = training.prepare_inputs(hr, lr, hr_mean, hr_std, hr_mean, hr_std, t, noise,
+                                                        cond_noise=cond_noise, cond_scale=0.05)
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(net(z_t, t, lr), hr)                      # :886-889
+        loss = training.mse_loss(net(z_t, t, lr_cond), hr_norm)                       # :886-889, fused with its gradient seed
         loss.backward()                                                               # :922 (+ DDP all-reduce)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                       # :926
         opt.step()
@@ -384,9 +390,10 @@ def train_main(a, K, W, rank, world, local):
                 "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "configs[3]: v3mod2 DiT 1280/28/20Q/4KV training step, batch 28 x [1024,1378] per GPU "
-                                       "(9660 token rows), AdamW(fused) + clip_grad_norm, MSE x-prediction loss",
-                           "norm": a.norm, "dropout": 0.0, "drop_path": 0.0,
-                           "note": "train-mode Dropout/DropPath are not implemented by the CUDA path yet (reference: 0.1 / 0.05)",
+                                       "(9660 token rows): normalise + cond-noise + flow-matching mix, forward (Dropout 0.1, DropPath 0.05), "
+                                       "MSE x-prediction loss, backward, clip_grad_norm_, AdamW(fused), bf16 weight re-pack",
+                           "norm": a.norm, "dropout": cfg["dropout"], "drop_path": cfg["drop_path_rate"],
+                           "cond_noise_ratio": 0.05,
                            "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU"},
                 "clocks": clk, "gpu_launches": int(launches), "loss": round(float(loss.item()), 5),
                 "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),

@@ -378,6 +378,27 @@ int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int co
 int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * The elementwise work either side of the model call in the training step (train_ddp_v3mod2.py:856-889,
+ * train_ddp_v3m2.py:547-585), one pass each instead of ~10 torch kernels and 8 `.item()` syncs.
+ *
+ * jat_train_inputs: all tensors f32 [B, C, T]; hr_mean / hr_std / lr_mean / lr_std f32 [C]; t, keep f32 [B].
+ *   hr_norm = (hr - hr_mean) / hr_std                                   (the regression target)
+ *   lr_cond = ((lr - lr_mean) / lr_std + cond_noise * s) * keep[b]      s = cond_scale (* *cond_scale_dev if non-NULL:
+ *             the adaptive variant's batch std stays on the device); cond_noise == NULL: no augmentation;
+ *             keep == NULL: no CFG condition dropout (keep[b] = 0 zeroes the condition of sample b)
+ *   z_t     = t[b] * hr_norm + (1 - t[b]) * noise
+ *   Unfused round-to-nearest fp32 in the reference's order: bit-identical to the torch expressions.
+ * jat_mse_loss: stats4 (DEVICE double[4], overwritten) = { sum (pred-target)^2, sum pred, sum pred^2, sum target^2 } over
+ *   n elements -- the MSE and the monitoring figures of :900-911 -- and, if d_pred != NULL, d_pred = (pred - target) * 2/n,
+ *   the gradient of mean((pred - target)^2) that seeds jat_dit_backward.
+ * -------------------------------------------------------------------------------------------- */
+int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, const float* hr_mean, const float* hr_std,
+                     const float* lr_mean, const float* lr_std, const float* noise, const float* cond_noise,
+                     const float* cond_scale_dev, float cond_scale, const float* keep, const float* t, float* hr_norm,
+                     float* lr_cond, float* z_t, int B, int C, int T, void* stream);
+int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Long-audio chunk plumbing (infer_test_v3m2.py:340-406 chunk loop, :188-233 crossfade_chunks).
  * A track latent[C, total_frames] (row pitch ld) is cut into chunks of `chunk_frames` frames starting every
  * `stride` = chunk_frames - overlap frames.

@@ -18,6 +18,7 @@
 #include "chunks.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
+#include "train_step.cuh"
 
 using namespace jat;
 
@@ -51,10 +52,11 @@ static const size_t kTailWsBytesPerSM = 128 * 256 * sizeof(float);
 static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify",
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
                                           "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm",
-                                          "gemm_accum", "gemm_dact", "adaln_bwd", "gate_bwd", "colsum_cast", "attention_bwd"};
+                                          "gemm_accum", "gemm_dact", "adaln_bwd", "gate_bwd", "colsum_cast", "attention_bwd",
+                                          "train_glue"};
 enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_CHUNKN = 9,
        TAG_XFADE = 10, TAG_GEMM_ACCUM = 11, TAG_GEMM_DACT = 12, TAG_ADALN_BWD = 13,
-       TAG_GATE_BWD = 14, TAG_COLSUM = 15, TAG_ATTN_BWD = 16, TAG_COUNT = 17 };
+       TAG_GATE_BWD = 14, TAG_COLSUM = 15, TAG_ATTN_BWD = 16, TAG_TRAIN_GLUE = 17, TAG_COUNT = 18 };
 
 static thread_local char g_err[512] = "";
 
@@ -663,6 +665,39 @@ extern "C" int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, 
     pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
     cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, (long long)n);
     return post_launch(ctx, "cast_f32_bf16");
+}
+
+// ------------------------------------------------------------------------------------------------ training-step glue
+extern "C" int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, const float* hr_mean, const float* hr_std,
+                                const float* lr_mean, const float* lr_std, const float* noise, const float* cond_noise,
+                                const float* cond_scale_dev, float cond_scale, const float* keep, const float* t, float* hr_norm,
+                                float* lr_cond, float* z_t, int B, int C, int T, void* stream) {
+    if (!ctx || !hr || !lr || !hr_mean || !hr_std || !lr_mean || !lr_std || !noise || !t || !hr_norm || !lr_cond || !z_t)
+        return fail(JAT_ERR_BAD_ARG, "jat_train_inputs: null argument");
+    if (B <= 0 || C <= 0 || T <= 0 || B > 65535 || C > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_train_inputs: bad B/C/T");
+    const uintptr_t al = (uintptr_t)hr | (uintptr_t)lr | (uintptr_t)noise | (uintptr_t)cond_noise | (uintptr_t)hr_norm |
+                         (uintptr_t)lr_cond | (uintptr_t)z_t;
+    if ((T & 3) == 0 && (al & 15) != 0) return fail(JAT_ERR_BAD_ARG, "jat_train_inputs: tensors must be 16-byte aligned");
+    dim3 grid((T / 4 + 255) / 256 > 0 ? (T / 4 + 255) / 256 : 1, C, B);
+    pre_launch(ctx, TAG_TRAIN_GLUE, (cudaStream_t)stream);
+    train_inputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hr, lr, hr_mean, hr_std, lr_mean, lr_std, noise, cond_noise,
+                                                                cond_scale_dev, cond_scale, keep, t, hr_norm, lr_cond, z_t, C, T);
+    return post_launch(ctx, "train_inputs");
+}
+
+extern "C" int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n,
+                            void* stream) {
+    if (!ctx || !pred || !target || !stats4 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: bad argument");
+    if ((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)d_pred) & 15) != 0)
+        return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: tensors must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    JAT_CUDA(cudaMemsetAsync(stats4, 0, 4 * sizeof(double), s));
+    long long want = (n / 4 + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 8;
+    const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    pre_launch(ctx, TAG_TRAIN_GLUE, s);
+    mse_loss_kernel<<<blocks, 256, 0, s>>>(pred, target, d_pred, stats4, (long long)n, (float)(2.0 / (double)n));
+    return post_launch(ctx, "mse_loss");
 }
 
 // ------------------------------------------------------------------------------------------------ chunks

@@ -71,7 +71,8 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     uint64_t* bar_mma2_done = bars + 7; // dV, dK, dQ MMAs retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp-uniform values through a full-mask shuffle: keeps the MMA issue path on the uniform datapath (elect_one())
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int kt = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int QT = (p.N + ATTB_TILE - 1) / ATTB_TILE;
     const int iters = p.G * QT;
@@ -92,7 +93,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
 
     if (warp == 0) {
@@ -116,7 +117,9 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // Warp-uniform control flow, one elected lane issues: the descriptors stay in uniform registers and the 32 MMAs
+        // of an iteration go out back to back (no per-instruction R2UR waterfall as under `lane == 0`).
+        {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
             constexpr uint32_t idesc_kv = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK: A K-major, B MN-major
             constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 1, 1);   // dQ: both MN-major
@@ -124,17 +127,22 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV));
             const uint64_t k_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sK), ATTB_TILE_BYTES);
             const uint64_t dst_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sdST), ATTB_TILE_BYTES);
+            const uint64_t pt_desc = umma_smem_desc_sw128(smem_u32(sPT));
+            const uint64_t dst_desc = umma_smem_desc_sw128(smem_u32(sdST));
             auto issue_first = [&](int it) {  // S^T = K Q^T, dP^T = V dO^T
                 const int st = it & 1;
                 mbar_wait(&bar_q_full[st], (uint32_t)((it >> 1) & 1));
                 tc_fence_after();
                 const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ + st * ATTB_TILE_BYTES));
                 const uint64_t do_desc = umma_smem_desc_sw128(smem_u32(sdO + st * ATTB_TILE_BYTES));
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_ST, k_desc + 2 * k, q_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
+                    for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_ST, k_desc + 2 * k, q_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_DPT, v_desc + 2 * k, do_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
-                umma_commit(bar_sp_full);
+                    for (int k = 0; k < 4; ++k) umma_bf16_ss<1>(tmem_base + COL_DPT, v_desc + 2 * k, do_desc + 2 * k, idesc_s, (uint32_t)(k != 0));
+                    umma_commit(bar_sp_full);
+                }
+                __syncwarp();
             };
             mbar_wait(bar_kv, 0);
             issue_first(0);
@@ -145,24 +153,28 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                 tc_fence_after();
                 const uint64_t q_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sQ + st * ATTB_TILE_BYTES), ATTB_TILE_BYTES);
                 const uint64_t do_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sdO + st * ATTB_TILE_BYTES), ATTB_TILE_BYTES);
+                const uint32_t acc0 = (uint32_t)(it != 0);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {  // reduction over the 128 queries of the tile, 16 per step
-                    const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
-                    umma_bf16_ss<1>(tmem_base + COL_DV, umma_smem_desc_sw128(smem_u32(sPT)) + a_off,
-                                    do_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv, (uint32_t)((it != 0) | (ks != 0)));
+                    for (int ks = 0; ks < 8; ++ks) {  // reduction over the 128 queries of the tile, 16 per step
+                        const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
+                        umma_bf16_ss<1>(tmem_base + COL_DV, pt_desc + a_off, do_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv,
+                                        ks == 0 ? acc0 : 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
+                        umma_bf16_ss<1>(tmem_base + COL_DK, dst_desc + a_off, q_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv,
+                                        ks == 0 ? acc0 : 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)  // reduction over the 128 keys of this CTA
+                        umma_bf16_ss<1>(tmem_base + COL_DQ, dst_desc_mn + (uint64_t)(ks * (2048 >> 4)),
+                                        k_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_dq, (uint32_t)(ks != 0));
+                    umma_commit(bar_mma2_done);
+                    umma_commit(&bar_q_empty[st]);
                 }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint64_t a_off = (uint64_t)((ks >> 2) * (ATTB_TILE_BYTES >> 4) + 2 * (ks & 3));
-                    umma_bf16_ss<1>(tmem_base + COL_DK, umma_smem_desc_sw128(smem_u32(sdST)) + a_off,
-                                    q_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_kv, (uint32_t)((it != 0) | (ks != 0)));
-                }
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)  // reduction over the 128 keys of this CTA
-                    umma_bf16_ss<1>(tmem_base + COL_DQ, dst_desc_mn + (uint64_t)(ks * (2048 >> 4)),
-                                    k_desc_mn + (uint64_t)(ks * (2048 >> 4)), idesc_dq, (uint32_t)(ks != 0));
-                umma_commit(bar_mma2_done);
-                umma_commit(&bar_q_empty[st]);
+                __syncwarp();
                 if (it + 1 < iters) issue_first(it + 1);
             }
         }

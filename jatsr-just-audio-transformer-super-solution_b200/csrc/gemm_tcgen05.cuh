@@ -81,8 +81,8 @@ __device__ __forceinline__ GemmWork gemm_decode_work(const GemmParams& p, int wo
         w.tile = p.head_tiles + t2; w.part = w2 - t2 * p.tail_splits; parts = p.tail_splits;
         w.tail = p.tail_splits > 1 ? t2 : -1;
     }
-    w.kb0 = (int)((long long)p.num_k_blocks * w.part / parts);
-    w.kb1 = (int)((long long)p.num_k_blocks * (w.part + 1) / parts);
+    if (parts == 1) { w.kb0 = 0; w.kb1 = p.num_k_blocks; }
+    else { w.kb0 = p.num_k_blocks * w.part / parts; w.kb1 = p.num_k_blocks * (w.part + 1) / parts; }
     return w;
 }
 
@@ -225,8 +225,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             const int num_work = gemm_num_work(p);
@@ -236,11 +236,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
                 const int a_row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM;
                 const int b_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
-                GEMM_TRACE(work / num_clusters, 0);
+                if (lane == 0) GEMM_TRACE(work / num_clusters, 0);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (elect_one()) {
                     if (p.dbg_skip != 0) {  // bandwidth diagnostics: stream only one (or neither) operand
                         const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : (uint32_t)Cfg::A_BYTES) + ((p.dbg_skip & 2) ? 0u : (uint32_t)Cfg::B_BYTES);
                         if (bytes == 0) { if (CG == 1 || cta_rank == 0) mbar_arrive(&bar_full[stage]); }
@@ -248,9 +249,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         else if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], bytes * 2);
                         if (!(p.dbg_skip & 1)) tma_load_tile<CG>(sa, &tmap_a, &bar_full[stage], kb * GEMM_BK, a_row0);
                         if (!(p.dbg_skip & 2)) tma_load_tile<CG>(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
+                    } else {
                     if (CG == 1) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
                     else if (cta_rank == 0) mbar_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES * 2);  // both CTAs' bytes
                     if constexpr (A_MN) {  // boxes of 64 reduction rows x 64 output rows (8 KB each)
@@ -267,6 +266,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     } else {
                         tma_load_tile<CG>(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
                     }
+                    }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -274,11 +276,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();  // reconverge before the (warp-aligned) teardown barrier
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (lane 0 issues; warp-uniform control)
-        // The tensor pipe has next to no queue: a tcgen05.mma issues only when the previous one is nearly done (issue cost
-        // ~= execution time, scripts/microbench_sm100.cu), so every instruction between two MMAs is a pipe bubble.  The
-        // path between the last MMA of a tile and the first of the next is therefore kept minimal: no work decoding
-        // (items of a launch without split-K all span the same k-blocks), and the next tile's accumulator-stage wait
-        // comes right after the commit, before the loop overhead.
+        // The whole warp runs the (uniform) control flow and ONE ELECTED lane issues: under elect.sync the descriptors stay
+        // in uniform registers and the four MMAs of a k-block go out back to back -- measured 512 clk per k-block, the
+        // tcgen05 rate.  (Under `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST waterfall:
+        // ~570-700 clk per k-block, more when the epilogue warps compete for issue slots.)  The path between the last MMA
+        // of a tile and the first of the next is kept minimal: no work decoding when every item spans all k-blocks.
         if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, A_MN, B_MN);
             // per 16-element k-step: +32 B inside the 128B swizzle atom (K-major) or +16 rows x 128 B (MN-major)

@@ -97,3 +97,60 @@ def test_training_step_runs_under_optimizer_and_is_repeatable():
     with torch.no_grad():
         e = torch.nn.functional.mse_loss(model(z_t, t, lr), hr).item()
     assert abs(e - losses[-1]) < 1e-3 * max(1.0, losses[-1])
+
+
+# ------------------------------------------------------------------------------------------------ f2: fused step glue
+@pytest.mark.parametrize("shape", [(3, 64, 1378), (2, 8, 87)])
+@pytest.mark.parametrize("variant", ["v3mod2", "v3m2_cfg_dropout", "adaptive", "plain"])
+def test_prepare_inputs_bit_exact(shape, variant):
+    """`training.prepare_inputs` against the reference's torch expressions (train_ddp_v3mod2.py:856-883,
+    train_ddp_v3m2.py:547-580), evaluated on the same device in fp32: bit-identical."""
+    from jat_b200 import training
+    B, C, T = shape
+    g = torch.Generator(device=dev()).manual_seed(5)
+    hr, lr, noise, cn = (torch.randn(B, C, T, generator=g, device=dev()) * s for s in (3.0, 2.0, 1.0, 1.0))
+    hr_mean, lr_mean = (torch.randn(1, C, 1, generator=g, device=dev()) for _ in range(2))
+    hr_std, lr_std = (torch.rand(1, C, 1, generator=g, device=dev()) + 0.5 for _ in range(2))
+    t = torch.rand(B, generator=g, device=dev())
+    ratio = 0.05
+    hr_norm = (hr - hr_mean) / hr_std
+    lr_norm = (lr - lr_mean) / lr_std
+    kw = {}
+    if variant in ("v3mod2", "v3m2_cfg_dropout"):
+        lr_norm = lr_norm + cn * (ratio * 1.0)
+        kw = dict(cond_noise=cn, cond_scale=ratio)
+    elif variant == "adaptive":
+        std = lr_norm.std().clamp(0.5, 2.0)
+        lr_norm = lr_norm + cn * (ratio * std)
+        kw = dict(cond_noise=cn, cond_scale=ratio, cond_scale_dev=std)
+    if variant == "v3m2_cfg_dropout":
+        mask = torch.tensor([True, False, True][:B], device=dev()).view(B, 1, 1)
+        lr_norm = lr_norm * (~mask).float()
+        kw["keep"] = (~mask).float()
+    tv = t.view(-1, 1, 1)
+    z_t = tv * hr_norm + (1 - tv) * noise
+    got = training.prepare_inputs(hr, lr, hr_mean, hr_std, lr_mean, lr_std, t, noise, **kw)
+    for name, a, b in zip(("hr_norm", "lr_cond", "z_t"), got, (hr_norm, lr_norm, z_t)):
+        assert torch.equal(a, b), (name, (a - b).abs().max().item())
+
+
+@pytest.mark.parametrize("n_shape", [(4, 64, 1378), (1, 3, 7)])
+def test_fused_mse_loss_matches_torch(n_shape):
+    from jat_b200 import training
+    g = torch.Generator(device=dev()).manual_seed(6)
+    pred = torch.randn(*n_shape, generator=g, device=dev()).requires_grad_(True)
+    target = torch.randn(*n_shape, generator=g, device=dev())
+    loss, stats = training.mse_loss(pred, target, return_stats=True)
+    (loss * 3.0).backward()
+    p2 = pred.detach().clone().requires_grad_(True)
+    want = torch.nn.functional.mse_loss(p2, target)
+    (want * 3.0).backward()
+    assert abs(loss.item() - want.item()) <= 2e-6 * abs(want.item())
+    assert rel_l2(pred.grad.cpu().numpy(), p2.grad.cpu().numpy()) < 1e-6
+    n = pred.numel()
+    s = stats.cpu().numpy()
+    assert abs(s[1] / n - pred.mean().item()) < 1e-5                                   # pred mean (:902)
+    assert abs((s[2] / n - (s[1] / n) ** 2) ** 0.5 - pred.std(unbiased=False).item()) < 1e-4
+    snr = 10 * np.log10(s[3] / s[0])                                                   # :905-908
+    want_snr = (10 * torch.log10((target ** 2).mean() / (((pred - target) ** 2).mean() + 1e-8))).item()
+    assert abs(snr - want_snr) < 1e-3
