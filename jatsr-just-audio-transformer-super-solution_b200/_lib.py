@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libjat_b200.so")
+LIB_PATH = os.environ.get("JAT_B200_LIB") or os.path.join(_HERE, "libjat_b200.so")  # env override: kernel experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "jat_b200.h")
 
 NVCC_FLAGS = [

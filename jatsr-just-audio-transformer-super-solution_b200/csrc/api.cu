@@ -105,6 +105,7 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->encode = (PFN_encodeTiled)fn;
     c->launches.store(0);
     c->gemm_cta_pair = 1;  // CTA pairs (cta_group::2) by default: half the B-operand smem traffic per SM
+    if (getenv("JAT_GEMM_CLUSTER")) c->gemm_cta_pair = atoi(getenv("JAT_GEMM_CLUSTER")) >= 2 ? 2 : 1;
     c->gemm_block_n = 0;
     c->profiling = false;
     c->ev_used = 0;
@@ -138,7 +139,7 @@ extern "C" int64_t jat_launch_count(const jat_ctx* ctx) { return ctx ? (int64_t)
 extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
     if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
     if (block_n != 0 && block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "block_n must be 0/128/256");
-    ctx->gemm_cta_pair = cta_pair ? 1 : 0;
+    ctx->gemm_cta_pair = cta_pair < 0 ? 1 : (cta_pair > 2 ? 2 : cta_pair);
     ctx->gemm_block_n = block_n;
     return 0;
 }
@@ -277,34 +278,74 @@ extern "C" int jat_drop_path_scales(jat_ctx* ctx, float* out, const float* rates
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0>
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1>
 static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                        const GemmParams& p, cudaStream_t s) {
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN>;
+    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN, MC>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    int clusters = ctx->sm_count / CG;
+    int clusters = ctx->sm_count / (CG * MC);
     const int num_work = p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
     if (clusters > num_work) clusters = num_work;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.gridDim = dim3((unsigned)(clusters * CG * MC));
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CG * MC;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if constexpr (MC > 1) {
+        // clusters of 4 must sit inside one GPC: fewer than sm_count / 4 may be co-resident; a persistent grid larger than
+        // that would run its surplus clusters as a second wave
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            cfg.gridDim = dim3((unsigned)(ctx->sm_count / (CG * MC) * CG * MC));
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) {
+                cudaGetLastError();
+                max_clusters = ctx->sm_count / (CG * MC);
+            }
+            if (getenv("JAT_DEBUG")) fprintf(stderr, "jat: max active clusters of %d CTAs: %d\n", CG * MC, max_clusters);
+        }
+        if (clusters > max_clusters) clusters = max_clusters;
+        cfg.gridDim = dim3((unsigned)(clusters * CG * MC));
+    }
     pre_launch(ctx, EPI <= EPI_UNPATCHIFY ? TAG_GEMM0 + EPI : (EPI == EPI_ACCUM ? TAG_GEMM_ACCUM : TAG_GEMM_DACT), s);
     JAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
     return post_launch(ctx, "gemm_tcgen05");
+}
+
+// forward (K-major) GEMMs on clusters of two CTA pairs with the W tile multicast between the pairs
+static int dispatch_gemm_mc2(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                             const GemmParams& p, const jat_gemm_epilogue* e, cudaStream_t s) {
+    switch (e->kind) {
+        case JAT_EPI_BIAS_ACT:
+            if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_F32)
+                return launch_gemm<256, 2, EPI_BIAS_ACT, ACT_NONE, 0, 0, 0, 2>(ctx, ta, tb, to, p, s);
+            if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<256, 2, EPI_BIAS_ACT, ACT_NONE, 1, 0, 0, 2>(ctx, ta, tb, to, p, s);
+            if (e->act == JAT_ACT_GELU_ERF && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<256, 2, EPI_BIAS_ACT, ACT_GELU, 1, 0, 0, 2>(ctx, ta, tb, to, p, s);
+            if (e->act == JAT_ACT_SILU && e->out_dtype == JAT_DTYPE_BF16)
+                return launch_gemm<256, 2, EPI_BIAS_ACT, ACT_SILU, 1, 0, 0, 2>(ctx, ta, tb, to, p, s);
+            break;
+        case JAT_EPI_QKV_ROPE:
+            return launch_gemm<256, 2, EPI_QKV_ROPE, ACT_NONE, 1, 0, 0, 2>(ctx, ta, tb, to, p, s);
+        case JAT_EPI_GATE_RESIDUAL:
+            return launch_gemm<256, 2, EPI_GATE_RESIDUAL, ACT_NONE, 0, 0, 0, 2>(ctx, ta, tb, to, p, s);
+        case JAT_EPI_UNPATCHIFY:
+            return launch_gemm<256, 2, EPI_UNPATCHIFY, ACT_NONE, 0, 0, 0, 2>(ctx, ta, tb, to, p, s);
+    }
+    return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: epilogue (%d, act %d, dtype %d) has no multicast-cluster variant", e->kind, e->act,
+                e->out_dtype);
 }
 
 template <int BN, int CG>
@@ -369,12 +410,17 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     if (block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: block_n must be 128 or 256");
     if (N % block_n != 0) block_n = 128;
     const int cg = cta_pair ? 2 : 1;
+    // cta_pair == 2: clusters of two CTA pairs sharing the W tile by TMA multicast (forward layouts, 256-wide tiles, no
+    // split-K); anything else falls back to independent CTA pairs
+    const bool dbg_skip_on = getenv("JAT_DBG_GEMM_SKIP") != nullptr && atoi(getenv("JAT_DBG_GEMM_SKIP")) != 0;
+    const int mc = (cta_pair == 2 && block_n == 256 && !a_mn && !w_mn && e->k_splits <= 1 && e->kind != JAT_EPI_ACCUM &&
+                    e->kind != JAT_EPI_DACT && M > 256 * (ctx->sm_count / 4) && !dbg_skip_on) ? 2 : 1;
 
     GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.num_n_blocks = N / block_n;
     p.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-    const int rows_per_tile = GEMM_BM * cg;
+    const int rows_per_tile = GEMM_BM * cg * mc;
     p.num_tiles = ((M + rows_per_tile - 1) / rows_per_tile) * p.num_n_blocks;
     p.bias = e->bias;
     p.out = e->out;
@@ -412,7 +458,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     {
         const int clusters = ctx->sm_count / cg;
         const int rem = p.num_tiles % clusters;
-        if (ctx->tail_split && p.k_splits == 1 && p.num_tiles > clusters && rem > 0) {
+        if (ctx->tail_split && mc == 1 && p.k_splits == 1 && p.num_tiles > clusters && rem > 0) {
             int splits = clusters / rem;
             if (splits > 8) splits = 8;
             if (splits > p.num_k_blocks / 2) splits = p.num_k_blocks / 2;
@@ -456,7 +502,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     if (a_mn) JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64));
     else JAT_TRY(make_tmap(ctx, &ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
     if (w_mn) JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 64));
-    else JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg)));
+    else JAT_TRY(make_tmap(ctx, &tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg / mc)));
     if (e->kind == JAT_EPI_UNPATCHIFY) {
         to = ta;  // unused by that epilogue
     } else {
@@ -466,6 +512,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
         JAT_TRY(make_tmap(ctx, &to, e->out, (uint64_t)M, (uint64_t)N, (uint64_t)e->ldo, 32, out_f32));
     }
     cudaStream_t s = (cudaStream_t)stream;
+    if (mc == 2) return dispatch_gemm_mc2(ctx, ta, tb, to, p, e, s);
     if (block_n == 256) {
         if (cg == 1) return dispatch_gemm_epi<256, 1>(ctx, ta, tb, to, p, e, s);
         return dispatch_gemm_epi<256, 2>(ctx, ta, tb, to, p, e, s);

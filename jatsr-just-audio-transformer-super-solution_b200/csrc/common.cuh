@@ -108,6 +108,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* tmap, uin
         : "memory");
 }
 
+// 2-CTA + cluster multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`; each destination's
+// completion is signalled on the barrier at this offset in the LEADER of that destination's CTA pair.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+        "[%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
 template <int kCtaGroup>
 __device__ __forceinline__ void tma_load_tile(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
     if constexpr (kCtaGroup == 1) tma_load_2d(dst, tmap, bar, c0, c1);

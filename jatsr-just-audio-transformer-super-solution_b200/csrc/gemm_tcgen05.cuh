@@ -122,7 +122,10 @@ struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 2 * GEMM_SLAB_BYTES;  // 64 KB
-    static constexpr int STAGES_RAW = (160 * 1024) / STAGE_BYTES;
+#ifndef JAT_GEMM_STAGE_BUDGET_KB
+#define JAT_GEMM_STAGE_BUDGET_KB 160
+#endif
+    static constexpr int STAGES_RAW = (JAT_GEMM_STAGE_BUDGET_KB * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -172,7 +175,10 @@ __device__ __forceinline__ void st_slab_chunk(uint32_t slab_row_addr, int lane, 
 //          wgrad  dW[N', K'] = dY^T[N', M] X[M, K']    -> A_MN and B_MN (token index = reduction index)
 // Tiles are then TMA boxes of 64 reduction rows x 64 elements (128 B), one box per 64 output rows/columns,
 // consumed through MN-major UMMA descriptors (leading byte offset = one 8 KB box).
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0>
+// MC = CTA pairs per cluster (CG == 2 only).  MC == 2: a cluster of 4 CTAs computes two 256-row M blocks of the same N block;
+// every CTA loads HALF of its pair's share of the W tile and multicasts it to the CTA with the same pair-rank in the other
+// pair, so the cluster reads W once instead of twice (the long-K GEMMs are bound by the L2 -> SM operand stream).
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -195,9 +201,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // that the MMA / TMA issue paths keep descriptors and addresses in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = (CG == 2) ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
-    const int cluster_id = blockIdx.x / CG;
-    const int num_clusters = gridDim.x / CG;
+    static_assert(MC == 1 || (CG == 2 && !A_MN && !B_MN), "multicast clusters: CTA pairs with K-major operands only");
+    const uint32_t cluster_rank = (CG == 2) ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
+    const uint32_t cta_rank = cluster_rank & 1u;   // rank inside the CTA pair (0 = leader: issues the MMAs)
+    const int pair = (int)(cluster_rank >> 1);     // which pair of the cluster (0 .. MC-1)
+    const int cluster_id = blockIdx.x / (CG * MC);
+    const int num_clusters = gridDim.x / (CG * MC);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -207,7 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], MC);  // a stage is free when the MMAs of every pair that reads it have retired
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tmem_full[a], 1);
@@ -234,7 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const GemmWork wk = gemm_decode_work(p, work);
                 const int tile = wk.tile, kb0 = wk.kb0, kb1 = wk.kb1;
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-                const int a_row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM;
+                const int a_row0 = ((m_blk * MC + pair) * CG + (int)cta_rank) * GEMM_BM;
                 const int b_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
                 if (lane == 0) GEMM_TRACE(work / num_clusters, 0);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -263,6 +272,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int j = 0; j < Cfg::B_ROWS / 64; ++j)
                             tma_load_tile<CG>(sb + j * 8192, &tmap_b, &bar_full[stage], b_row0 + j * 64, kb * GEMM_BK);
+                    } else if constexpr (MC == 2) {
+                        // my half of this pair-rank's W rows, to both CTAs of the cluster with this pair-rank
+                        constexpr int PART = Cfg::B_ROWS / 2;
+                        tma_load_2d_2sm_mc(sb + pair * PART * 128, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0 + pair * PART,
+                                           (uint16_t)(cta_rank ? 0xAu : 0x5u));
                     } else {
                         tma_load_tile<CG>(sb, &tmap_b, &bar_full[stage], kb * GEMM_BK, b_row0);
                     }
@@ -307,10 +321,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int k = 0; k < GEMM_BK / 16; ++k)
                             umma_bf16_ss<CG>(d_tmem, a_desc + a_kstep * k, b_desc + b_kstep * k, idesc, (uint32_t)((i | k) != 0));
                         if constexpr (CG == 1) umma_commit(&bar_empty[stage]);
-                        else umma_commit_2sm(&bar_empty[stage], 0x3);
+                        else umma_commit_2sm(&bar_empty[stage], MC == 2 ? 0xF : 0x3);
                         if (i + 1 == nkb) {
                             if constexpr (CG == 1) umma_commit(&bar_tmem_full[as]);
-                            else umma_commit_2sm(&bar_tmem_full[as], 0x3);
+                            else umma_commit_2sm(&bar_tmem_full[as], (uint16_t)(0x3 << (2 * pair)));
                             GEMM_TRACE(work / num_clusters, 3);
                         }
                     }
@@ -340,7 +354,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // split-K (reduce-add epilogues): the bias goes in with the first partial sum; tail split: with the fix-up
             const bool add_bias = p.bias != nullptr && (wk.part == 0 || wk.tail >= 0);
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-            const int row0 = (m_blk * CG + (int)cta_rank) * GEMM_BM + quad * 32;  // first row of this warp's slab
+            const int row0 = ((m_blk * MC + pair) * CG + (int)cta_rank) * GEMM_BM + quad * 32;  // first row of this warp's slab
             const int m = row0 + lane;
             const bool row_ok = m < p.M;
             const int n_base = n_blk * BN + wg * HALF;
@@ -372,7 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 int last = 0;
                 if (lane == 0) {
                     if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
-                    else mbar_arrive_cluster(&bar_tmem_empty[as], 0);
+                    else mbar_arrive_cluster(&bar_tmem_empty[as], cluster_rank & ~1u);
                     int* cnt = p.tail_cnt + (wk.tail * CG + (int)cta_rank) * GEMM_EPI_WARPS + (warp - 4);
                     last = atomicAdd(cnt, 1) == p.tail_splits - 1;
                     if (last) *cnt = 0;  // every part has arrived: reset for the next launch
@@ -605,7 +619,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (warp == 4 && lane == 0) GEMM_TRACE(work / num_clusters, 6);
             if (lane == 0) {
                 if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
-                else mbar_arrive_cluster(&bar_tmem_empty[as], 0);
+                else mbar_arrive_cluster(&bar_tmem_empty[as], cluster_rank & ~1u);
             }
             if ((as ^= 1) == 0) aphase ^= 1;
         }

@@ -87,7 +87,7 @@ def bench_gemm(iters):
             out = torch.empty(B, 1024, 1378, device=dev)
         else:
             out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
-        for cta_pair in (0, 1):
+        for cta_pair in (0, 1, 2):
             for bn in (256, 128):
                 fn = lambda: ops.gemm(A, W, bias=bias if kw["kind"] != L.EPI_QKV_ROPE else None, out=out,
                                       cta_pair=cta_pair, block_n=bn, **kw)

@@ -300,6 +300,44 @@ def test_gemm_tail_split_matches_unsplit_and_is_deterministic(ops, L, cta_pair, 
         assert rel_l2(split[lo:], want) < 1e-4
 
 
+@pytest.mark.parametrize("kind", ["bias_f32", "bias_gelu_bf16", "qkv_rope", "gate_residual", "unpatchify"])
+@pytest.mark.parametrize("M", [19320, 9660])
+def test_gemm_multicast_cluster_is_bit_identical(ops, L, kind, M):
+    """cta_pair = 2: clusters of two CTA pairs, the W tile multicast between the pairs (one L2 read instead of two).  The
+    per-element accumulation order is unchanged, so the result equals the independent-pair schedule bit for bit."""
+    Ntok = 345
+    B = M // Ntok
+    shapes = {"bias_f32": (1280, 512), "bias_gelu_bf16": (5120, 1280), "qkv_rope": (1792, 1280), "gate_residual": (1280, 5120),
+              "unpatchify": (4096, 1280)}
+    N, K = shapes[kind]
+    A, W, bias = _ab(M, N, K, seed=13)
+    cos, sin = _rope_tables()
+    gate = torch.randn(B, N, device=dev())
+    x0 = torch.randn(M, N, device=dev())
+
+    def run(cta_pair):
+        if kind == "bias_f32":
+            return ops.gemm(A, W, bias=bias, out_dtype=L.DTYPE_F32, cta_pair=cta_pair, block_n=256)
+        if kind == "bias_gelu_bf16":
+            return ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, cta_pair=cta_pair, block_n=256)
+        if kind == "qkv_rope":
+            return ops.gemm(A, W, kind=L.EPI_QKV_ROPE, tokens_per_batch=Ntok, rope_cos=cos, rope_sin=sin, rope_cols=1536,
+                            cta_pair=cta_pair, block_n=256)
+        if kind == "gate_residual":
+            x = x0.clone()
+            ops.gemm(A, W, kind=L.EPI_GATE_RESIDUAL, out=x, bias=bias, gate=gate, gate_batch_stride=N,
+                     tokens_per_batch=Ntok, cta_pair=cta_pair, block_n=256)
+            return x
+        out = torch.full((B, N // 4, 1378), float("nan"), device=dev())
+        ops.gemm(A, W, kind=L.EPI_UNPATCHIFY, out=out, bias=bias, tokens_per_batch=Ntok, patch_len=4, t_out=1378,
+                 cta_pair=cta_pair, block_n=256)
+        return out
+    want = run(1)
+    got = run(2)
+    assert torch.isfinite(got.float()).all()
+    assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
+
+
 # ------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 16, 4), (2, 256, 4, 4), (1, 352, 5, 1)])
 def test_gqa_attention(ops, B, N, Hq, Hkv):
