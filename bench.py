@@ -62,6 +62,34 @@ def step_work(Beff=2 * B):
     return w, total_flops
 
 
+def ncu_traffic(kernel_class):
+    """DRAM bytes per launch of a kernel class from the committed ncu `--set full` capture (None if absent)."""
+    import re
+    epi = {"gemm_bias_act": 0, "gemm_qkv_rope": 1, "gemm_gate_residual": 2, "gemm_unpatchify": 3}
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1b_ncu_full_summary.json")))
+    except Exception:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for items in d.values():
+        for it in items:
+            name = it.get("Kernel Name", "")
+            m = re.search(r"gemm_tcgen05_kernel<(\d+), (\d+), (\d+)", name)
+            hit = (m and epi.get(kernel_class) == int(m.group(3))) or (not m and kernel_class.replace("_fwd", "") in name)
+            if not hit:
+                continue
+            try:
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = it[k].split()
+                    tot += float(v) * unit[u]
+                vals.append(tot)
+            except Exception:
+                pass
+    return round(sum(vals) / len(vals)) if vals else None
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -246,8 +274,10 @@ def main():
         kernels[name] = ent
     top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     roof = {k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-    roof.update(kernel=top, peak_source=f"MEASURED_PEAKS.json sustained ({pkz['src']})", traffic=None,
+    roof.update(kernel=top, peak_source=f"MEASURED_PEAKS.json sustained ({pkz['src']})", traffic=ncu_traffic(top),
                 share_of_step=kernels[top]["share"])
+    roof["traffic_source"] = ("profiles/r1b_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                              "(ncu --set full, cold cache), mean over the launches of this class in the capture")
 
     # ---- e2e through the public sampler API with host buffers
     e2e = None

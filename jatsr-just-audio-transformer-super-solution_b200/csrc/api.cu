@@ -214,6 +214,25 @@ extern "C" int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, d
     return n;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait() in common.cuh): ONLY for kernels that call pdl_wait()
+// before their first global-memory access.  OFF by default: measured on the sampling step it is 1-2 % SLOWER than plain
+// stream order (the successor's early-resident CTAs cost more than the ~3 us launch gaps they hide); JAT_PDL=1 enables it.
+static bool pdl_enabled() {
+    static const bool on = getenv("JAT_PDL") && atoi(getenv("JAT_PDL")) != 0;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 2D tensor map: `rows` x `cols` (cols contiguous), row pitch ld elements; box = box_rows x box_cols with
 // box_cols * elem_bytes == 128 bytes, 128-byte swizzle, out-of-bounds elements read as zero / not written.
 static int make_tmap(jat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
@@ -296,13 +315,15 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG * MC;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if constexpr (MC > 1) {
         // clusters of 4 must sit inside one GPC: fewer than sm_count / 4 may be co-resident; a persistent grid larger than
         // that would run its surplus clusters as a second wave
@@ -529,8 +550,8 @@ static int launch_adaln(jat_ctx* ctx, const float* x, __nv_bfloat16* out, const 
     const int nv = (nvec + 31) / 32;
     dim3 grid((M + ADALN_WARPS - 1) / ADALN_WARPS), block(ADALN_WARPS * 32);
     pre_launch(ctx, TAG_ADALN, s);
-#define JAT_ADALN_CASE(NV)                                                                                       \
-    adaln_norm_modulate_kernel<NV, NORM><<<grid, block, 0, s>>>(x, out, shift, scale, bstride, weight, eps, M, D, ntok)
+#define JAT_ADALN_CASE(NV) \
+    launch_pdl(adaln_norm_modulate_kernel<NV, NORM>, grid, block, 0, s, x, out, shift, scale, bstride, weight, eps, M, D, ntok)
     if (nv <= 4) JAT_ADALN_CASE(4);
     else if (nv <= 8) JAT_ADALN_CASE(8);
     else if (nv <= 10) JAT_ADALN_CASE(10);
@@ -572,8 +593,8 @@ extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, c
     const int N = (T + P - 1) / P;
     dim3 grid((N + PATCH_TN - 1) / PATCH_TN, 2 * C / PATCH_TC, B);
     pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
-    patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, xt_batch, x_cond, cond_batch,
-                                                                 (__nv_bfloat16*)out_bf16, C, T, N, 2 * C * 4);
+    launch_pdl(patchify_cast_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x_t, xt_batch, x_cond, cond_batch,
+               (__nv_bfloat16*)out_bf16, C, T, N, 2 * C * 4);
     return post_launch(ctx, "patchify_cast");
 }
 
@@ -584,7 +605,8 @@ extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16,
     const int N = (T + P - 1) / P;
     dim3 grid((N + PATCH_TN - 1) / PATCH_TN, C / PATCH_TC, B);
     pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
-    patchify_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, nullptr, 0, (__nv_bfloat16*)out_bf16, C, T, N, C * 4);
+    launch_pdl(patchify_cast_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, B, (const float*)nullptr, 0,
+               (__nv_bfloat16*)out_bf16, C, T, N, C * 4);
     return post_launch(ctx, "patchify_single");
 }
 
@@ -593,7 +615,7 @@ extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf1
     if (B <= 0 || D < 4 || D % 2 != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_timestep_features: bad B/D");
     dim3 grid((D / 2 + 127) / 128, B);
     pre_launch(ctx, TAG_TSTEP, (cudaStream_t)stream);
-    timestep_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out_bf16, B, D);
+    launch_pdl(timestep_features_kernel, grid, dim3(128), 0, (cudaStream_t)stream, t, (__nv_bfloat16*)out_bf16, B, D);
     return post_launch(ctx, "timestep_features");
 }
 
@@ -605,8 +627,8 @@ extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, co
     long long cap = (long long)ctx->sm_count * 8;
     int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     pre_launch(ctx, TAG_EULER, (cudaStream_t)stream);
-    cfg_euler_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, x_c, x_u, cfg_scale, t_dt, step,
-                                                                       (long long)numel);
+    launch_pdl(cfg_euler_update_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, z, x_c, x_u, cfg_scale, t_dt, step,
+               (long long)numel);
     return post_launch(ctx, "cfg_euler_update");
 }
 
@@ -800,7 +822,7 @@ static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv
         configured = true;
     }
     pre_launch(ctx, TAG_ATTN, s);
-    gqa_attention_fwd_kernel<NKH, DROP><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tkv, p);
+    launch_pdl(gqa_attention_fwd_kernel<NKH, DROP>, grid, dim3(ATT_THREADS), Cfg::SMEM_BYTES, s, tq, tkv, p);
     return post_launch(ctx, "gqa_attention_fwd");
 }
 

@@ -119,6 +119,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int k_col = (p.Hq + g) * ATT_HD;
     const int v_col = (p.Hq + p.Hkv + g) * ATT_HD;
 
+    pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     if (threadIdx.x == 0) ATT_TRACE(127);
     if (warp == 12) {
         if (lane == 0) {

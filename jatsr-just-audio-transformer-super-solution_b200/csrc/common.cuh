@@ -148,6 +148,14 @@ __device__ __forceinline__ void tma_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ----------------------------------------------------------------------------------- programmatic dependent launch
+// Kernels of the forward path are launched with programmaticStreamSerializationAllowed: a kernel may begin (block
+// scheduling, barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining its
+// last wave.  pdl_wait() blocks until the predecessor grid has completed and its writes are visible -- every such kernel
+// calls it before its first global-memory access; pdl_launch_dependents() lets the successor start its own preamble.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(ADALN_WARPS * 32)
 adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                            const float* __restrict__ shift, const float* __restrict__ scale, long long mod_bstride,
                            const float* __restrict__ weight, float eps, int M, int D, int tokens_per_batch) {
+    pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const int row = blockIdx.x * ADALN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256)
 patchify_cast_kernel(const float* __restrict__ x_t, int xt_batch, const float* __restrict__ x_cond, int cond_batch,
                      __nv_bfloat16* __restrict__ out, int C, int T, int N, int K) {
     __shared__ __align__(16) float tile[PATCH_TC][PATCH_ROW];
+    pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const int n0 = blockIdx.x * PATCH_TN;
     const int c0 = blockIdx.y * PATCH_TC;  // in [0, 2C)
     const int b = blockIdx.z;
@@ -137,6 +139,7 @@ patchify_cast_kernel(const float* __restrict__ x_t, int xt_batch, const float* _
 // scaled by 1000.  Uses accurate sinf/cosf/expf: arguments are < 1 rad * 1, tiny kernel.
 // ------------------------------------------------------------------------------------------------
 __global__ void timestep_features_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int D) {
+    pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const int half = D >> 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -166,6 +169,7 @@ __device__ __forceinline__ float euler_one(float z, float xc, float xu, bool has
 __global__ void __launch_bounds__(256)
 cfg_euler_update_kernel(float* __restrict__ z, const float* __restrict__ x_c, const float* __restrict__ x_u,
                         float cfg_scale, const float* __restrict__ t_dt, int step, long long numel) {
+    pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const float t = t_dt[2 * step], dt = t_dt[2 * step + 1];
     const bool direct = !(t < 0.999f);
     const float den = __fadd_rn(__fsub_rn(1.0f, t), 1e-5f);

@@ -232,6 +232,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_launch_dependents();
+    pdl_wait();  // everything above overlapped the predecessor's tail; operands / outputs are touched only from here on
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one elected lane issues)
