@@ -22,7 +22,7 @@
 
 namespace jat {
 
-constexpr int ATTB_THREADS = 256;
+constexpr int ATTB_THREADS = 384;  // 4 service warps + 8 compute warps (two per SM sub-partition)
 constexpr int ATTB_TILE = 128;
 constexpr int ATTB_TILE_BYTES = ATTB_TILE * 128;  // [128 rows x 64 bf16]
 constexpr int ATTB_SMEM_BYTES = 2 * ATTB_TILE_BYTES          // K, V
@@ -82,7 +82,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         mbar_init(bar_kv, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_q_full[i], 1); mbar_init(&bar_q_empty[i], 1); }
         mbar_init(bar_sp_full, 1);
-        mbar_init(bar_pds_full, 128);
+        mbar_init(bar_pds_full, 256);
         mbar_init(bar_mma2_done, 1);
         fence_barrier_init();
     }
@@ -181,8 +181,11 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ compute warps: thread = key row
+        // Two warps per TMEM lane quadrant (= per SM sub-partition): group 0 (warps 4-7) takes queries [0, 64) of a tile,
+        // group 1 (warps 8-11) queries [64, 128); one warp's MUFU / TMEM-load latency hides behind the other's.
+        const int grp = (warp - 4) >> 2;
         const int r = (warp & 3) * 32 + lane;
-        const int t = threadIdx.x - 128;  // 0..127, == r
+        const int t = threadIdx.x - 128;  // 0..255; t & 127 == r
         const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int key = kt * ATTB_TILE + r;
         const bool key_ok = key < p.N;
@@ -194,9 +197,9 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         auto dq_epilogue = [&](int it) {  // dQ tile of iteration `it`: TMEM -> f32 smem boxes -> TMA reduce-add
             const int h = g * p.G + it / QT, qt = it % QT;
             if (t == 0) tma_store_wait_read<0>();  // the previous reduce-add has drained the staging tile
-            named_bar(1, 128);
-#pragma unroll
-            for (int bx = 0; bx < 2; ++bx) {
+            named_bar(1, 256);
+            {
+                const int bx = grp;  // each group moves one 32-column box of the [128 x 64] dQ tile
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + COL_DQ + bx * 32, v);
                 tmem_ld_wait();
@@ -209,7 +212,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            named_bar(1, 128);
+            named_bar(1, 256);
             if (t == 0) {
                 tma_reduce_add_2d(&tmap_dq, sdQ, h * ATT_HD, row_b + qt * ATTB_TILE);
                 tma_reduce_add_2d(&tmap_dq, sdQ + ATTB_TILE_BYTES, h * ATT_HD + 32, row_b + qt * ATTB_TILE);
@@ -221,7 +224,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         for (int it = 0; it < iters; ++it) {
             const int h = g * p.G + it / QT, qt = it % QT;
             const int slot = it & 1;
-            {   // per-query statistics of this tile (queries past the batch item's N tokens get lse = +inf -> P = 0)
+            if (grp == 0) {  // per-query statistics of this tile (queries past the batch item's N tokens get lse = +inf -> P = 0)
                 const int q = qt * ATTB_TILE + t;
                 const bool q_ok = q < p.N;
                 const long long idx = ((long long)b * p.Hq + h) * p.N + q;
@@ -233,14 +236,14 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                 tc_fence_after();
                 dq_epilogue(it - 1);   // (its named barriers also publish s_lse / s_dsum)
             } else {
-                named_bar(1, 128);
+                named_bar(1, 256);
             }
             mbar_wait(bar_sp_full, (uint32_t)(it & 1));
             tc_fence_after();
             const float* lse_t = s_lse + slot * ATTB_TILE;
             const float* ds_t = s_dsum + slot * ATTB_TILE;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {  // 32 queries at a time
+            for (int c = 2 * grp; c < 2 * grp + 2; ++c) {  // 32 queries at a time
                 uint32_t sv[32], dv[32];
                 tmem_ld_32x32(t_row + COL_ST + c * 32, sv);
                 tmem_ld_32x32(t_row + COL_DPT + c * 32, dv);
@@ -286,6 +289,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         {   // (tcgen05.ld is warp-collective: every lane loads, only rows that hold a real key store)
             __nv_bfloat16* orow = p.dqkv + (long long)(row_b + (key_ok ? key : 0)) * ((p.Hq + 2 * p.Hkv) * ATT_HD);
             uint32_t lo[32], hi[32];
+            if (grp == 0) {  // group 0 writes dV, group 1 dK
             tmem_ld_32x32(t_row + COL_DV, lo);
             tmem_ld_32x32(t_row + COL_DV + 32, hi);
             tmem_ld_wait();
@@ -301,6 +305,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                         pack_bf16(__uint_as_float(hi[j + 4]), __uint_as_float(hi[j + 5])), pack_bf16(__uint_as_float(hi[j + 6]), __uint_as_float(hi[j + 7])));
                 }
             }
+            } else {
             tmem_ld_32x32(t_row + COL_DK, lo);
             tmem_ld_32x32(t_row + COL_DK + 32, hi);
             tmem_ld_wait();
@@ -323,6 +328,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                     *reinterpret_cast<uint4*>(ok + 32 + j) = make_uint4(pack_bf16(rb[j], rb[j + 1]), pack_bf16(rb[j + 2], rb[j + 3]),
                                                                         pack_bf16(rb[j + 4], rb[j + 5]), pack_bf16(rb[j + 6], rb[j + 7]));
                 }
+            }
             }
         }
         if (t == 0) tma_store_wait_all<0>();
