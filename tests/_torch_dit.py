@@ -29,8 +29,9 @@ def _rope(x, cos, sin):
     return x * c + torch.cat([-x2, x1], -1) * s
 
 
-def dit_forward(p, cfg, x_t, t, x_cond, rms=False, masks=None):
-    """p: {state_dict key: tensor (requires_grad ok)}; returns x_pred [B, C, T]."""
+def dit_forward(p, cfg, x_t, t, x_cond, rms=False, masks=None, blocks_out=None):
+    """p: {state_dict key: tensor (requires_grad ok)}; returns x_pred [B, C, T].  blocks_out: optional list that receives
+    the residual stream [B*N, D] after every block (what forward hooks on model.blocks[i] see in the reference)."""
     D, depth, P = cfg["hidden_size"], cfg["depth"], cfg["patch_len"]
     Hq, Hkv = cfg["num_q_heads"], cfg["num_kv_heads"]
     B, C, T = x_t.shape
@@ -78,7 +79,33 @@ def dit_forward(p, cfg, x_t, t, x_cond, rms=False, masks=None):
         if masks is not None and masks.get("path") is not None:
             br = br * masks["path"][i, 1][:, None, None]
         x = x + br
+        if blocks_out is not None:
+            blocks_out.append(x.detach().reshape(B * N, D))
     x = _norm(x, p.get("final_layer.0.weight"), rms)
     x = x @ p["final_layer.1.weight"].T + p["final_layer.1.bias"]
     x = x.view(B, N, C, P).permute(0, 2, 1, 3).reshape(B, C, N * P)
     return x[:, :, :T]
+
+
+@torch.no_grad()
+def flow_matching_sample(p, cfg, lr_latent, z0, num_steps=50, cfg_scale=3.0, rms=False):
+    """The reference sampler (infer_test_v3m2.py:108-185) on the restatement above, z0 injected."""
+    B = lr_latent.shape[0]
+    z = z0.clone()
+    ts = torch.linspace(0.0, 1.0, num_steps + 1, device=z.device)
+    for i in range(num_steps):
+        t_curr, t_next = ts[i], ts[i + 1]
+        dt = t_next - t_curr
+        tb = torch.full((B,), float(t_curr), device=z.device)
+        if cfg_scale != 1.0:
+            out = dit_forward(p, cfg, torch.cat([z, z]), torch.cat([tb, tb]), torch.cat([lr_latent, torch.zeros_like(lr_latent)]),
+                              rms=rms)
+            x_c, x_u = out[:B], out[B:]
+            x = x_u + cfg_scale * (x_c - x_u)
+        else:
+            x = dit_forward(p, cfg, z, tb, lr_latent, rms=rms)
+        if float(t_curr) < 0.999:
+            z = z + (x - z) / (1 - t_curr + 1e-5) * dt
+        else:
+            z = x
+    return z

@@ -191,3 +191,27 @@ def test_torch_restatement_with_masks_matches_reference(cls_idx, rms):
     torch.nn.functional.mse_loss(want, hr).backward()
     for k, prm in model.named_parameters():
         assert rel_l2(params[k].grad.numpy(), prm.grad.numpy()) < 2e-4, k
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference not mounted")
+def test_torch_restatement_sampler_matches_reference_sampler():
+    """tests/_torch_dit.flow_matching_sample (the fp32 truth of the full-size GPU parity test) == the reference's
+    flow_matching_sample (infer_test_v3m2.py:108-185) under the same seed, CFG and no-CFG."""
+    import torch
+    from tests._torch_dit import flow_matching_sample as restated
+    ref_cls, _, ref_sampler = import_reference()
+    cfg = dict(input_channels=16, cond_channels=16, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
+               bottleneck_dim=64, mlp_ratio=2.0, dropout=0.0, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = rerandomise_zero_init(ref_cls(**cfg), bf16_exact=False).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    lr = torch.randn(2, 16, 30, generator=torch.Generator().manual_seed(1))
+    for scale in (3.0, 1.0):
+        torch.manual_seed(42)
+        z0 = torch.randn(2, 16, 30)
+        torch.manual_seed(42)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = ref_sampler(model, lr, num_steps=7, cfg_scale=scale, device="cpu", verbose=False)
+        got = restated(sd, cfg, lr, z0, num_steps=7, cfg_scale=scale)
+        assert rel_l2(got.numpy(), want.numpy()) < 1e-5, scale
