@@ -142,12 +142,21 @@ int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64
  * on the packed projection buffer written by the QKV_ROPE GEMM:
  *   qkv bf16 [B * N, (Hq + 2*Hkv) * 64] = [ Q heads | K heads | V heads ],   out bf16 [B * N, Hq*64].
  * No mask, bidirectional. K/V of one KV head are staged in shared memory once per CTA and reused
- * by the Hq/Hkv query heads of the group. head_dim must be 64; N <= 352.
+ * by the Hq/Hkv query heads of the group. head_dim must be 64.  One launch covers up to 352 keys (the S row of a query tile
+ * lives in one TMEM accumulator, so the softmax is exact); longer sequences -- the reference allows up to 2048 tokens,
+ * jat_audiosr_v2.py:428 -- go through jat_gqa_attention_fwd_long: one launch per 352-key chunk into caller scratch, then a
+ * merge by the chunks' log-sum-exps (jat_attention_passes(N) chunks).
  * lse_or_null: optional f32 [B, Hq, N] output, log2(sum_j 2^(s_ij * log2(e) / 8)) per query row, kept by the training
  * forward for jat_gqa_attention_bwd.
  * -------------------------------------------------------------------------------------------- */
 int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, float* lse_or_null, int B, int N, int Hq,
                           int Hkv, int head_dim, void* stream);
+int jat_attention_passes(int N); /* ceil(N / 352) */
+/* Any N: part_o bf16 [passes, B*N, Hq*64] and part_lse f32 [passes, B, Hq, N] are scratch (may be NULL when N <= 352);
+ * drop_p / drop_seed as in jat_gqa_attention_fwd_dropout (mask column = global key index). */
+int jat_gqa_attention_fwd_long(jat_ctx* ctx, const void* qkv_bf16, void* out_bf16, float* lse_or_null, void* part_o_bf16,
+                               float* part_lse, int B, int N, int Hq, int Hkv, int head_dim, float drop_p, uint32_t drop_seed,
+                               void* stream);
 
 /* Backward of jat_gqa_attention_fwd.  d_out / out bf16 [B*N, Hq*64] (gradient of, and the saved, forward
  * output), lse from the forward call.  Writes dqkv bf16 [B*N, (Hq+2Hkv)*64] = gradient w.r.t. the PRE-RoPE q | k | v
@@ -241,6 +250,8 @@ typedef struct jat_dit_workspace {
     void* t_act;    /* bf16 [Bt, hidden]      SiLU(t_emb) */
     float* mod;     /* f32  [Bt, depth*6*hidden]  all blocks' shift/scale/gate */
     float* block_out; /* optional f32 [depth, M, hidden] per-block residual snapshots for parity tests, or NULL */
+    void* attn_part;  /* N > 352 tokens only: bf16 [jat_attention_passes(N), M, hidden] per-key-chunk attention outputs */
+    float* lse_part;  /* N > 352 tokens only: f32 [jat_attention_passes(N), B, Hq, N] */
 } jat_dit_workspace;
 
 /* Timestep path only: t f32 [Bt] -> ws->mod [Bt, depth*6*hidden] (t_embedder + every block's

@@ -88,7 +88,7 @@ class DitWorkspace(C.Structure):
         ("patches", C.c_void_p), ("pe_hid", C.c_void_p), ("x", C.c_void_p), ("h", C.c_void_p),
         ("qkv", C.c_void_p), ("attn", C.c_void_p), ("mlp_hid", C.c_void_p),
         ("t_feat", C.c_void_p), ("t_hid", C.c_void_p), ("t_act", C.c_void_p), ("mod", C.c_void_p),
-        ("block_out", C.c_void_p),
+        ("block_out", C.c_void_p), ("attn_part", C.c_void_p), ("lse_part", C.c_void_p),
     ]
 
 
@@ -110,6 +110,8 @@ SIGNATURES = {
     "jat_dropout_site_seed": (_u32, [_u64, _i, _i]),
     "jat_dropout_scale_mask": (_i, [_vp, _vp, _i64, _i, _f, _u32, _vp]),
     "jat_drop_path_scales": (_i, [_vp, _vp, _vp, _i, _i, _u64, _vp]),
+    "jat_attention_passes": (_i, [_i]),
+    "jat_gqa_attention_fwd_long": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32, _vp]),
     "jat_gqa_attention_fwd_dropout": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32, _vp]),
     "jat_gqa_attention_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32,
                                            _vp]),

@@ -831,41 +831,72 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, f
     return jat_gqa_attention_fwd_dropout(ctx, qkv, out, lse, B, N, Hq, Hkv, head_dim, 0.0f, 0u, stream);
 }
 
-extern "C" int jat_gqa_attention_fwd_dropout(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq,
-                                             int Hkv, int head_dim, float drop_p, uint32_t drop_seed, void* stream) {
-    if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
-    if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
-    if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
-        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: bad B/N/heads");
-    if (N > ATT_MAX_NK)
-        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: N = %d tokens > %d not supported by the single-pass kernel", N,
-                    ATT_MAX_NK);
+// one launch of the single-pass kernel on keys [key0, key0 + nkeys) of every batch item
+static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq, int Hkv, int key0,
+                          int nkeys, const DropCfg& drop, cudaStream_t s) {
     AttnParams p = {};
     p.B = B; p.N = N; p.Hq = Hq; p.Hkv = Hkv; p.G = Hq / Hkv;
+    p.key0 = key0; p.NKeys = nkeys;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.trace = ctx->att_trace;
-    if (!make_drop(drop_p, drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: drop_p must be in [0, 1)");
-    if ((long long)B * Hq * N > 0xffffffffll) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: B*Hq*N exceeds 2^32");
+    p.drop = drop;
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
-    cudaStream_t s = (cudaStream_t)stream;
     // key range padded to NK = 2*NKH columns (two softmax warpgroups); padded keys are masked in-kernel
     if (p.drop.thresh != 0u) {
-        if (N <= 64) return launch_attention<32, true>(ctx, tq, qkv, rows, cols, p, grid, s);
-        if (N <= 128) return launch_attention<64, true>(ctx, tq, qkv, rows, cols, p, grid, s);
-        if (N <= 192) return launch_attention<96, true>(ctx, tq, qkv, rows, cols, p, grid, s);
-        if (N <= 256) return launch_attention<128, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (nkeys <= 64) return launch_attention<32, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (nkeys <= 128) return launch_attention<64, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (nkeys <= 192) return launch_attention<96, true>(ctx, tq, qkv, rows, cols, p, grid, s);
+        if (nkeys <= 256) return launch_attention<128, true>(ctx, tq, qkv, rows, cols, p, grid, s);
         return launch_attention<176, true>(ctx, tq, qkv, rows, cols, p, grid, s);
     }
-    if (N <= 64) return launch_attention<32>(ctx, tq, qkv, rows, cols, p, grid, s);
-    if (N <= 128) return launch_attention<64>(ctx, tq, qkv, rows, cols, p, grid, s);
-    if (N <= 192) return launch_attention<96>(ctx, tq, qkv, rows, cols, p, grid, s);
-    if (N <= 256) return launch_attention<128>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (nkeys <= 64) return launch_attention<32>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (nkeys <= 128) return launch_attention<64>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (nkeys <= 192) return launch_attention<96>(ctx, tq, qkv, rows, cols, p, grid, s);
+    if (nkeys <= 256) return launch_attention<128>(ctx, tq, qkv, rows, cols, p, grid, s);
     return launch_attention<176>(ctx, tq, qkv, rows, cols, p, grid, s);
+}
+
+extern "C" int jat_gqa_attention_fwd_dropout(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq,
+                                             int Hkv, int head_dim, float drop_p, uint32_t drop_seed, void* stream) {
+    if (N > ATT_MAX_NK)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: N = %d tokens > %d needs the chunked form jat_gqa_attention_fwd_long "
+                    "(scratch for the per-chunk partial results)", N, ATT_MAX_NK);
+    return jat_gqa_attention_fwd_long(ctx, qkv, out, lse, nullptr, nullptr, B, N, Hq, Hkv, head_dim, drop_p, drop_seed, stream);
+}
+
+extern "C" int jat_attention_passes(int N) { return N <= 0 ? 0 : (N + ATT_MAX_NK - 1) / ATT_MAX_NK; }
+
+extern "C" int jat_gqa_attention_fwd_long(jat_ctx* ctx, const void* qkv, void* out, float* lse, void* part_o, float* part_lse,
+                                          int B, int N, int Hq, int Hkv, int head_dim, float drop_p, uint32_t drop_seed,
+                                          void* stream) {
+    if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
+    if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
+    if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: bad B/N/heads");
+    if ((long long)B * Hq * N > 0xffffffffll) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: B*Hq*N exceeds 2^32");
+    DropCfg drop;
+    if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: drop_p must be in [0, 1)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int passes = jat_attention_passes(N);
+    if (passes == 1) return attention_pass(ctx, qkv, out, lse, B, N, Hq, Hkv, 0, N, drop, s);
+    if (!part_o || !part_lse)
+        return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd_long: N = %d needs part_o (bf16 [%d, B*N, Hq*64]) and part_lse "
+                    "(f32 [%d, B, Hq, N])", N, passes, passes);
+    const long long o_pass = (long long)B * N * Hq * ATT_HD, l_pass = (long long)B * Hq * N;
+    for (int c = 0; c < passes; ++c) {
+        const int key0 = c * ATT_MAX_NK, nk = N - key0 < ATT_MAX_NK ? N - key0 : ATT_MAX_NK;
+        JAT_TRY(attention_pass(ctx, qkv, (__nv_bfloat16*)part_o + c * o_pass, part_lse + c * l_pass, B, N, Hq, Hkv, key0, nk, drop, s));
+    }
+    const long long warps = (long long)B * N * Hq;
+    pre_launch(ctx, TAG_ATTN, s);
+    attention_combine_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)part_o, part_lse,
+                                                                                 (__nv_bfloat16*)out, lse, B, N, Hq, passes);
+    return post_launch(ctx, "attention_combine");
 }
 
 extern "C" int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv, const void* d_out, const void* out, const float* lse,
@@ -977,7 +1008,8 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
         e.kind = JAT_EPI_QKV_ROPE; e.out = ws->qkv; e.ldo = QKV; e.tokens_per_batch = N;
         e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (w->n_q_heads + w->n_kv_heads) * 64;
         JAT_TRY(jat_gemm_bf16(ctx, ws->h, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
-        JAT_TRY(jat_gqa_attention_fwd(ctx, ws->qkv, ws->attn, nullptr, B, N, w->n_q_heads, w->n_kv_heads, 64, stream));
+        JAT_TRY(jat_gqa_attention_fwd_long(ctx, ws->qkv, ws->attn, nullptr, ws->attn_part, ws->lse_part, B, N, w->n_q_heads,
+                                           w->n_kv_heads, 64, 0.0f, 0u, stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
         e.gate = m + 2 * D; e.gate_batch_stride = mod_batch_stride;
@@ -1068,8 +1100,9 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
         e.kind = JAT_EPI_QKV_ROPE; e.out = qkv; e.ldo = QKV; e.tokens_per_batch = N;
         e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (Hq + Hkv) * 64;
         JAT_TRY(jat_gemm_bf16(ctx, h1, D, w->wqkv[i], D, M, QKV, D, &e, -1, 0, stream));
-        JAT_TRY(jat_gqa_attention_fwd_dropout(ctx, qkv, attn, (float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), B, N, Hq, Hkv, 64,
-                                              pd, jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
+        JAT_TRY(jat_gqa_attention_fwd_long(ctx, qkv, attn, (float*)at(sv->lse, i, (int64_t)B * Hq * N, 4), ws->attn_part,
+                                           ws->lse_part, B, N, Hq, Hkv, 64, pd,
+                                           jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_GATE_RESIDUAL; e.out = ws->x; e.ldo = D; e.tokens_per_batch = N;
         e.gate = m + 2 * D; e.gate_batch_stride = NM; e.aux = at(sv->y1, i, MD, 2); e.ld_aux = D;

@@ -61,6 +61,8 @@ struct AttCfg {
 
 struct AttnParams {
     int B, N, Hq, Hkv, G;
+    int key0, NKeys;    // this launch attends to keys [key0, key0 + NKeys) of every batch item (NKeys <= 2 * NKH); longer
+                        // sequences run one launch per key chunk and are merged by attention_combine_kernel
     __nv_bfloat16* out;
     float* lse;         // optional f32 [B, Hq, N]: log2-domain log-sum-exp of the scaled scores (kept for the backward pass)
     float scale_log2e;  // (1/sqrt(64)) * log2(e)
@@ -115,7 +117,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int q_row0 = b * p.N + qt * ATT_BQ;  // global token row of this tile's first query
-    const int kv_row0 = b * p.N;
+    const int kv_row0 = b * p.N + p.key0;
     const int k_col = (p.Hq + g) * ATT_HD;
     const int v_col = (p.Hq + p.Hkv + g) * ATT_HD;
 
@@ -312,7 +314,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tc_fence_before();
             mbar_arrive(&bar_s_free[half]);
             {   // mask the padded keys: only the 16-column chunks that reach past the last real key (warp-uniform)
-                const int nvalid = p.N - col0;
+                const int nvalid = p.NKeys - col0;
 #pragma unroll
                 for (int c = 0; c < NKH / 16; ++c) {
                     if (nvalid < (c + 1) * 16) {
@@ -346,7 +348,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const float e3 = ex2_approx(fmaf(__uint_as_float(s[j + 3]), sl2, -moff));
                 a4[0] += e0; a4[1] += e1; a4[2] += e2; a4[3] += e3;
                 if constexpr (DROP) {
-                    const uint32_t kc = (uint32_t)(col0 + j);
+                    const uint32_t kc = (uint32_t)(p.key0 + col0 + j);
                     pk[j / 2] = pack_bf16(e0 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc),
                                           e1 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 1));
                     pk[j / 2 + 1] = pack_bf16(e2 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 2),
@@ -381,6 +383,39 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, 512);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merge of the per-key-chunk passes of a long sequence (N > 352 tokens): pass c produced O_c = softmax_c(S_c) V_c and
+// lse_c = log2 sum_j 2^(s_ij) over its keys; then  O = sum_c 2^(lse_c - lse) O_c,  lse = log2 sum_c 2^lse_c.
+// One warp per (token row, head), lane = 2 of the 64 head columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attention_combine_kernel(const __nv_bfloat16* __restrict__ part_o, const float* __restrict__ part_lse, __nv_bfloat16* __restrict__ out,
+                         float* __restrict__ lse, int B, int N, int Hq, int passes) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long M = (long long)B * N;
+    if (w >= M * Hq) return;
+    const int h = (int)(w % Hq);
+    const long long m = w / Hq;
+    const int b = (int)(m / N), n = (int)(m % N);
+    const long long lse_idx = ((long long)b * Hq + h) * N + n, lse_pass = (long long)B * Hq * N;
+    float mx = -INFINITY;
+    for (int c = 0; c < passes; ++c) mx = fmaxf(mx, __ldg(part_lse + c * lse_pass + lse_idx));
+    float den = 0.f;
+    for (int c = 0; c < passes; ++c) den += exp2f(__ldg(part_lse + c * lse_pass + lse_idx) - mx);
+    const float inv = 1.0f / den;
+    float a0 = 0.f, a1 = 0.f;
+    const long long o_idx = m * ((long long)Hq * ATT_HD) + (long long)h * ATT_HD + lane * 2, o_pass = M * Hq * ATT_HD;
+    for (int c = 0; c < passes; ++c) {
+        const float wgt = exp2f(__ldg(part_lse + c * lse_pass + lse_idx) - mx) * inv;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(part_o + c * o_pass + o_idx);
+        a0 = fmaf(__uint_as_float(v << 16), wgt, a0);
+        a1 = fmaf(__uint_as_float(v & 0xffff0000u), wgt, a1);
+    }
+    *reinterpret_cast<uint32_t*>(out + o_idx) = pack_bf16(a0, a1);
+    if (lse != nullptr && lane == 0) lse[lse_idx] = mx + log2f(den);
 }
 
 }  // namespace jat

@@ -215,10 +215,16 @@ class Workspace:
             t_feat=bf(Bt, D), t_hid=bf(Bt, D), t_act=bf(Bt, D), mod=f32(Bt, depth * 6 * D),
         )
         self.block_out = f32(depth, M, D) if keep_blocks else None
+        # sequences of more than 352 tokens: the attention runs one pass per 352-key chunk and merges the partial results
+        passes = L.load().jat_attention_passes(N)
+        self.attn_part = bf(passes, M, D) if passes > 1 else None
+        self.lse_part = f32(passes, B, attn0.num_q_heads, N) if passes > 1 else None
         s = self.struct = L.DitWorkspace()
         for k, v in self.buf.items():
             setattr(s, k, v.data_ptr())
         s.block_out = self.block_out.data_ptr() if keep_blocks else None
+        s.attn_part = self.attn_part.data_ptr() if passes > 1 else None
+        s.lse_part = self.lse_part.data_ptr() if passes > 1 else None
         self.mod = self.buf["mod"]
 
 

@@ -119,8 +119,17 @@ def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None, drop_
     assert qkv.shape == (B * N, (Hq + 2 * Hkv) * head_dim)
     if out is None:
         out = torch.empty(B * N, Hq * head_dim, dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().jat_gqa_attention_fwd_dropout(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, Hq, Hkv,
-                                                   head_dim, float(drop_p), int(drop_seed), _stream(qkv.device)))
+    lib = L.load()
+    passes = lib.jat_attention_passes(N)
+    if passes <= 1:
+        L.check(lib.jat_gqa_attention_fwd_dropout(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, Hq, Hkv,
+                                                  head_dim, float(drop_p), int(drop_seed), _stream(qkv.device)))
+        return out
+    part_o = torch.empty(passes, B * N, Hq * head_dim, dtype=torch.bfloat16, device=qkv.device)
+    part_lse = torch.empty(passes, B, Hq, N, dtype=torch.float32, device=qkv.device)
+    L.check(lib.jat_gqa_attention_fwd_long(_ctx(qkv), qkv.data_ptr(), out.data_ptr(), _p(lse), part_o.data_ptr(),
+                                           part_lse.data_ptr(), B, N, Hq, Hkv, head_dim, float(drop_p), int(drop_seed),
+                                           _stream(qkv.device)))
     return out
 
 

@@ -357,10 +357,40 @@ def test_gqa_attention(ops, B, N, Hq, Hkv):
     assert rel_l2(got.float(), want) < 8e-3
 
 
-def test_gqa_attention_rejects_long(ops, L):
+def test_gqa_attention_single_pass_entry_rejects_long(ops, L):
+    """The scratch-free entry point covers one 352-key chunk; longer sequences must use jat_gqa_attention_fwd_long."""
+    import ctypes as C
     qkv = torch.zeros(400, 3 * 64, dtype=torch.bfloat16, device=dev())
-    with pytest.raises(L.JatError):
-        ops.gqa_attention_fwd(qkv, 1, 400, 1, 1)
+    out = torch.zeros(400, 64, dtype=torch.bfloat16, device=dev())
+    rc = L.load().jat_gqa_attention_fwd(L.context(0), qkv.data_ptr(), out.data_ptr(), None, 1, 400, 1, 1, 64,
+                                        torch.cuda.current_stream().cuda_stream)
+    assert rc == -2 and b"jat_gqa_attention_fwd_long" in L.load().jat_last_error()
+
+
+@pytest.mark.parametrize("B,N,Hq,Hkv", [(1, 353, 4, 2), (2, 400, 8, 4), (1, 704, 5, 1), (1, 1000, 4, 4), (1, 2048, 2, 1)])
+def test_gqa_attention_long_sequences(ops, B, N, Hq, Hkv):
+    """More than 352 tokens (the reference allows 2048, jat_audiosr_v2.py:428): one pass per 352-key chunk merged by the
+    chunks' log-sum-exps == the full softmax; the merged LSE feeds the (length-agnostic) backward kernel."""
+    torch.manual_seed(9)
+    hd = 64
+    G = Hq // Hkv
+    cos, sin = _bwd_rope_tables(N)
+    raw = (torch.randn(B, N, Hq + 2 * Hkv, hd, device=dev()) * 1.2).to(torch.bfloat16).float().requires_grad_(True)
+    q = _bwd_rope(raw[:, :, :Hq], cos, sin)
+    k = _bwd_rope(raw[:, :, Hq:Hq + Hkv], cos, sin)
+    v = raw[:, :, Hq + Hkv:]
+    qkv = torch.cat([q, k, v], 2).detach().reshape(B * N, -1).to(torch.bfloat16)
+    lse = torch.empty(B, Hq, N, device=dev())
+    got = ops.gqa_attention_fwd(qkv, B, N, Hq, Hkv, lse=lse)
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k.repeat_interleave(G, dim=2)) / 8.0
+    o = torch.einsum("bhnm,bmhd->bnhd", torch.softmax(s, -1), v.repeat_interleave(G, dim=2)).reshape(B * N, Hq * hd)
+    assert rel_l2(got.float(), o.detach()) < 1e-2
+    assert (lse - torch.logsumexp(s, -1).detach() * math.log2(math.e)).abs().max() < 2e-2
+    d_out = torch.randn(B * N, Hq * hd, device=dev()).to(torch.bfloat16)
+    dq = ops.gqa_attention_bwd(qkv, d_out, got, lse, cos, sin, B, N, Hq, Hkv).float().view(B, N, Hq + 2 * Hkv, hd)
+    o.backward(d_out.float())
+    for name, sl in (("dq", slice(0, Hq)), ("dk", slice(Hq, Hq + Hkv)), ("dv", slice(Hq + Hkv, Hq + 2 * Hkv))):
+        assert rel_l2(dq[:, :, sl], raw.grad[:, :, sl]) < 2e-2, name
 
 
 def test_gqa_attention_extreme_scores(ops):

@@ -172,3 +172,27 @@ def test_max_len_raises_value_error():
     x = torch.zeros(1, 32, 4 * 2049, device=dev())
     with pytest.raises(ValueError):
         model(x, torch.zeros(1, device=dev()), x)
+
+
+@pytest.mark.parametrize("cls", ["JaT_AudioSR_V2", "JaT_AudioSR_V3"])
+def test_forward_long_sequence_matches_oracle(cls):
+    """T = 2000 frames -> N = 500 tokens (> 352: the chunked attention path inside the whole-model plan), eval forward
+    against the numpy oracle; and the training forward + backward run at that length."""
+    from oracle import dit_oracle as O
+    cfg = dict(hidden_size=256, depth=2, num_q_heads=4, num_kv_heads=2, bottleneck_dim=128, input_channels=64, cond_channels=64)
+    model = build(cls, cfg, seed=21)
+    g = torch.Generator().manual_seed(4)
+    B, T = 2, 2000
+    x, c, t = torch.randn(B, 64, T, generator=g), torch.randn(B, 64, T, generator=g), torch.rand(B, generator=g)
+    w = {k: v.detach().float().cpu().numpy() for k, v in model.state_dict().items()}
+    want = O.dit_forward(w, x.numpy(), t.numpy(), c.numpy(), num_q_heads=4, num_kv_heads=2, patch_len=4)
+    model = model.to(dev())
+    got = model(x.to(dev()), t.to(dev()), c.to(dev()))
+    assert rel_l2(got.cpu().numpy(), want) < 1.5e-2
+    model.train()
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
+    model.dropout_p = 0.0
+    out = model(x.to(dev()), t.to(dev()), c.to(dev()))
+    out.float().pow(2).mean().backward()
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in model.parameters())
