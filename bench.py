@@ -179,8 +179,9 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the K timed steps from one captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
-                    help="sample = headline CFG denoise step (configs[2]); train = DDP training step (configs[3])")
+    ap.add_argument("--mode", default="sample", choices=["sample", "train", "long"],
+                    help="sample = headline CFG denoise step (configs[2]); train = DDP training step (configs[3]); "
+                         "long = 10-minute track, chunked 50-step CFG inference sharded over the GPUs (configs[4])")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -195,6 +196,8 @@ def main():
         return reference_arm(a, K, W, rank, world, config)
     if a.mode == "train":
         return train_main(a, K, W, rank, world, local)
+    if a.mode == "long":
+        return long_main(a, K, W, rank, world, local)
 
     import torch
     import jat_b200
@@ -429,6 +432,69 @@ def train_main(a, K, W, rank, world, local):
                 "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),
                 "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),
                 "kernels": kernels, "kernel_ms_per_step": round(tot / pk, 2)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def long_main(a, K, W, rank, world, local):
+    """BASELINE configs[4]: a 10-minute track (latent [1024, 51679] at 86.13 frames/s) cut into 43 chunks of 1378 frames
+    (overlap 172, infer_test_v3m2.py:340-348), the chunks dealt round-robin over the GPUs, each GPU denoising its chunks as
+    ONE batch with 50 CFG = 3.0 steps, all-gather of the finished chunk latents, crossfade + de-normalise
+    (`jat_b200.chunked.sample_long`).  One "step" = the whole track; value = audio seconds per wall second."""
+    import torch
+    import jat_b200
+    from jat_b200 import chunked
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", init_method="env://")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    model = build_model(dev, a.norm)
+    seconds, frames = 600.0, 51679
+    g = torch.Generator().manual_seed(5)
+    track = (torch.randn(C, frames, generator=g) * 2.0 + 0.3).pin_memory()
+    mean, std = torch.full((C,), 0.3), torch.full((C,), 2.0)
+
+    def run():
+        out = chunked.sample_long(model, track.to(dev, non_blocking=True), mean, std, mean, std, num_steps=50, cfg_scale=CFG_SCALE,
+                                  device=dev)
+        return out.cpu() if rank == 0 else out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    for _ in range(max(W, 1)):
+        run()
+    barrier()
+    clocks = ClockSampler(local)
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = run()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    if rank == 0:
+        assert out.shape == (1, C, frames) and torch.isfinite(out).all()
+        n_chunks = len(chunked.plan_chunks(frames))
+        line = {"metric": "long-audio chunked inference: audio seconds per second (10-minute track, 50-step CFG=3.0)",
+                "value": round(K * seconds / (ms / 1e3), 1), "unit": "audio s/s", "n_gpus": world, "steps": K, "warmup": max(W, 1),
+                "ms_per_step": round(ms / K, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"configs[4]: 10-minute track = latent [1024, {frames}] -> {n_chunks} chunks of 1378 frames "
+                                       f"(overlap 172), round-robin over {world} GPU(s), 50 Euler steps CFG=3.0 per chunk batch, "
+                                       "all-gather + crossfade + de-normalise; host track in, host latent out",
+                           "norm": a.norm, "chunks": n_chunks, "chunks_per_gpu": -(-n_chunks // world)},
+                "clocks": clk, "wall_s": round(wall, 3)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
