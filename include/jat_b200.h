@@ -170,8 +170,9 @@ int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv_bf16, const void* d_out_
  * Train-mode stochastic regularisers.  The reference draws nn.Dropout(p) masks on the attention probabilities
  * (jat_audiosr_v2.py:158), after the MLP's GELU (:250) and after mlp.3 (:252), and a per-sample DropPath factor on
  * each gated branch (:21-34, :281, :287) from torch's global Philox stream.  Here every mask element is a pure function
- * of (site seed, row, col): KEEP iff hash(row, col, site_seed) >= round(p * 2^32), kept values scaled by 1/(1-p) -- so the
- * backward kernels regenerate the forward's masks instead of storing them, and the same Bernoulli(1-p) statistics hold.
+ * of (site seed, row, col): one 32-bit hash of (row, col >> 1, site_seed) gives the two 16-bit lanes of columns col & ~1
+ * and col | 1; KEEP iff lane >= round(p * 2^16), kept values scaled by 1 / (1 - round(p 2^16) / 2^16) -- so the backward
+ * kernels regenerate the forward's masks instead of storing them, with Bernoulli(1-p) statistics (p exact to 2^-17).
  * Site seeds: jat_dropout_site_seed(seed, block, site).  Mask coordinates: attention (row = (b*Hq + h)*N + query,
  * col = key); MLP sites (row = token row m, col = feature).
  * -------------------------------------------------------------------------------------------- */

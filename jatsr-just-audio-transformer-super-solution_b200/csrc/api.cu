@@ -269,9 +269,9 @@ static bool make_drop(float p, uint32_t seed, DropCfg* d) {
     d->thresh = 0u; d->seed = seed; d->inv_keep = 1.0f;
     if (!(p >= 0.0f) || p >= 1.0f) return false;
     if (p == 0.0f) return true;
-    double th = (double)p * 4294967296.0;
-    d->thresh = th >= 4294967295.0 ? 4294967295u : (th < 1.0 ? 1u : (uint32_t)(th + 0.5));
-    d->inv_keep = 1.0f / (1.0f - p);
+    double th = (double)p * 65536.0 + 0.5;  // 16-bit lanes: two mask elements per hash (common.cuh: drop_scale)
+    d->thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
+    d->inv_keep = (float)(1.0 / (1.0 - (double)d->thresh / 65536.0));
     return true;
 }
 

@@ -349,10 +349,11 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 a4[0] += e0; a4[1] += e1; a4[2] += e2; a4[3] += e3;
                 if constexpr (DROP) {
                     const uint32_t kc = (uint32_t)(p.key0 + col0 + j);
-                    pk[j / 2] = pack_bf16(e0 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc),
-                                          e1 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 1));
-                    pk[j / 2 + 1] = pack_bf16(e2 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 2),
-                                              e3 * drop_scale(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 3));
+                    float m0, m1, m2, m3;  // kc is even: two keys per hash
+                    drop_scale2(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc, m0, m1);
+                    drop_scale2(p.drop, drop_row + (uint32_t)h * (uint32_t)p.N, kc + 2, m2, m3);
+                    pk[j / 2] = pack_bf16(e0 * m0, e1 * m1);
+                    pk[j / 2 + 1] = pack_bf16(e2 * m2, e3 * m3);
                 } else {
                     pk[j / 2] = pack_bf16(e0, e1);
                     pk[j / 2 + 1] = pack_bf16(e2, e3);

@@ -194,8 +194,10 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
         float4 dm = d;
         if (drop.thresh != 0u) {  // forward: y = dropout(acc + bias) entered x through the gate
             const uint32_t rr = (uint32_t)(row0 + n), cc = (uint32_t)(c4 * 4);
-            dm.x *= drop_scale(drop, rr, cc); dm.y *= drop_scale(drop, rr, cc + 1);
-            dm.z *= drop_scale(drop, rr, cc + 2); dm.w *= drop_scale(drop, rr, cc + 3);
+            float m0, m1, m2, m3;
+            drop_scale2(drop, rr, cc, m0, m1);
+            drop_scale2(drop, rr, cc + 2, m2, m3);
+            dm.x *= m0; dm.y *= m1; dm.z *= m2; dm.w *= m3;
         }
         a_sum.x += dm.x; a_sum.y += dm.y; a_sum.z += dm.z; a_sum.w += dm.w;
         const float4 o = make_float4(dm.x * g4.x, dm.y * g4.y, dm.z * g4.z, dm.w * g4.w);

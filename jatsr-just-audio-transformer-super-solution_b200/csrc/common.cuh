@@ -344,21 +344,37 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_major
 }
 
 // ----------------------------------------------------------------------------------- dropout RNG
-// Counter-based Bernoulli masks for train-mode Dropout (jat_audiosr_v2.py:158, 250, 252): element (row, col) of
-// site `seed` is KEPT iff hash(row, col, seed) >= thresh, thresh = round(p * 2^32).  Stateless, so the backward
-// kernels regenerate exactly the forward's mask from the same (row, col, seed); tests rebuild it in torch.
-__host__ __device__ __forceinline__ uint32_t jat_hash3(uint32_t row, uint32_t col, uint32_t seed) {
+// Counter-based Bernoulli masks for train-mode Dropout (jat_audiosr_v2.py:158, 250, 252).  One 32-bit hash of
+// (row, col >> 1, site seed) serves the TWO elements (row, col & ~1) and (row, col | 1): each takes one 16-bit lane and is
+// KEPT iff lane >= thresh, thresh = round(p * 2^16) (effective p within 2^-17 of the requested one; kept values are
+// scaled by 1 / (1 - thresh / 2^16), so the expectation is exact).  Stateless: the backward kernels regenerate exactly the
+// forward's mask from the same (row, col, seed); tests materialise it with jat_dropout_scale_mask.  The hash (2 IMAD + XOR,
+// then two multiply / xor-shift rounds) passes the rate / independence battery of tests/test_dropout_gpu.py.
+__host__ __device__ __forceinline__ uint32_t jat_hash3(uint32_t row, uint32_t col, uint32_t seed) {  // DropPath factors
     uint32_t h = (row * 0x9E3779B1u) ^ ((col + seed) * 0x85EBCA77u);
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
     return h;
 }
+__host__ __device__ __forceinline__ uint32_t jat_hash_pair(uint32_t row, uint32_t colpair, uint32_t seed) {
+    uint32_t h = (row * 0x9E3779B1u + seed) ^ (colpair * 0x85EBCA77u);
+    h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
 struct DropCfg {
-    uint32_t thresh;  // 0 = dropout off
+    uint32_t thresh;  // 16-bit lane threshold; 0 = dropout off
     uint32_t seed;
-    float inv_keep;   // 1 / (1 - p)
+    float inv_keep;   // 1 / (1 - thresh / 65536)
 };
 __device__ __forceinline__ float drop_scale(const DropCfg& d, uint32_t row, uint32_t col) {
-    return jat_hash3(row, col, d.seed) >= d.thresh ? d.inv_keep : 0.0f;
+    const uint32_t h = jat_hash_pair(row, col >> 1, d.seed);
+    const uint32_t lane = (col & 1u) ? (h >> 16) : (h & 0xffffu);
+    return lane >= d.thresh ? d.inv_keep : 0.0f;
+}
+// the two elements (row, col), (row, col + 1) of an EVEN col from one hash
+__device__ __forceinline__ void drop_scale2(const DropCfg& d, uint32_t row, uint32_t col_even, float& m0, float& m1) {
+    const uint32_t h = jat_hash_pair(row, col_even >> 1, d.seed);
+    m0 = (h & 0xffffu) >= d.thresh ? d.inv_keep : 0.0f;
+    m1 = (h >> 16) >= d.thresh ? d.inv_keep : 0.0f;
 }
 
 // ----------------------------------------------------------------------------------- math / packing

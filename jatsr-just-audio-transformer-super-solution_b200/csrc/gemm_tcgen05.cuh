@@ -448,7 +448,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 }
                                 if (p.drop.thresh != 0u) {
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) f[q] *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q));
+                                    for (int q = 0; q < 8; q += 2) {
+                                        float m0, m1;
+                                        drop_scale2(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q), m0, m1);
+                                        f[q] *= m0; f[q + 1] *= m1;
+                                    }
                                 }
                             } else {
                                 if (use_aux)
@@ -459,7 +463,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 for (int q = 0; q < 8; ++q) f[q] = apply_act<ACT>(f[q]);
                                 if (p.drop.thresh != 0u) {
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) f[q] *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q));
+                                    for (int q = 0; q < 8; q += 2) {
+                                        float m0, m1;
+                                        drop_scale2(p.drop, (uint32_t)m, (uint32_t)(n0 + hx * 32 + j + q), m0, m1);
+                                        f[q] *= m0; f[q + 1] *= m1;
+                                    }
                                 }
                             }
                             st_slab_chunk(slab_row[buf], lane, hx * 4 + j / 8, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
@@ -499,10 +507,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                               r2 = __uint_as_float(v[j + 2]) + b4.z, r3 = __uint_as_float(v[j + 3]) + b4.w;
                         if constexpr (EPI == EPI_GATE_RESIDUAL) {
                             if (p.drop.thresh != 0u) {
-                                r0 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j));
-                                r1 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 1));
-                                r2 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 2));
-                                r3 *= drop_scale(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 3));
+                                float m0, m1, m2, m3;
+                                drop_scale2(p.drop, (uint32_t)m, (uint32_t)(n0 + j), m0, m1);
+                                drop_scale2(p.drop, (uint32_t)m, (uint32_t)(n0 + j + 2), m2, m3);
+                                r0 *= m0; r1 *= m1; r2 *= m2; r3 *= m3;
                             }
                             if (p.aux != nullptr && row_ok)  // training forward keeps y = acc + bias (bf16) for the gate gradient
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.aux)) +

@@ -53,7 +53,8 @@ def test_mask_is_bernoulli_and_sites_are_independent(ops, L, p):
     sigma = math.sqrt(p * (1 - p) / n)
     for m in ms:
         vals = torch.unique(m)
-        assert vals.numel() == 2 and vals[0] == 0 and abs(vals[1].item() - 1 / (1 - p)) < 1e-6
+        p_eff = round(p * 65536) / 65536  # 16-bit lanes: the effective rate is within 2^-17 of the requested one
+        assert vals.numel() == 2 and vals[0] == 0 and abs(vals[1].item() - 1 / (1 - p_eff)) < 1e-6
         keep = (m != 0).float().mean().item()
         assert abs(keep - (1 - p)) < 6 * sigma, (keep, 1 - p)
         # per-row and per-column keep rates: no structure along either axis
