@@ -1140,11 +1140,16 @@ static int wgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* X, int
     e.a_transposed = 1; e.w_transposed = 1;
     const int bn = (Kin % 256 == 0) ? 256 : 128;
     const long long tiles = (long long)((Nout + 255) / 256) * (Kin / bn);
-    long long want = (2LL * (ctx->sm_count / 2) + tiles - 1) / tiles;
     const int kblocks = (Mtok + GEMM_BK - 1) / GEMM_BK;
-    if (want > 8) want = 8;
-    if (want > kblocks) want = kblocks;
-    e.k_splits = (int)(want < 1 ? 1 : want);
+    // split the token reduction s ways so that the persistent schedule's makespan is shortest: every CTA pair runs
+    // ceil(tiles * s / pairs) items of ceil(kblocks / s) k-blocks each, plus ~4 k-blocks' worth of f32 reduce-add epilogue
+    const long long pairs = ctx->sm_count / 2;
+    long long best = 1, best_cost = -1;
+    for (long long sp = 1; sp <= 8 && sp <= kblocks; ++sp) {
+        const long long cost = ((tiles * sp + pairs - 1) / pairs) * ((kblocks + sp - 1) / sp + 4);
+        if (best_cost < 0 || cost < best_cost) { best = sp; best_cost = cost; }
+    }
+    e.k_splits = (int)best;
     return jat_gemm_bf16(ctx, dY, ld_dy, X, ld_x, Nout, Kin, Mtok, &e, -1, 0, stream);
 }
 // input gradient  dX[Mtok, Kin] = dY[Mtok, Nout] W[Nout, Kin]  (W as stored), optional * act'(u)

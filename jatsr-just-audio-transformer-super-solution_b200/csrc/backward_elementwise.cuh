@@ -50,6 +50,12 @@ adaln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restric
         xv[i] = idx < nvec ? __ldcs(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         gv[i] = idx < nvec ? bf16x4_to_f32(__ldcs(gr + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (accumulate) {  // the old dx row is only needed after two warp reductions: pull it towards L2 now
+        const float4* dxp = reinterpret_cast<const float4*>(dx + (long long)row * D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (lane + 32 * i < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(dxp + lane + 32 * i));
+    }
     float mean = 0.f, rstd;
     if constexpr (NORM_KIND == 0) {
         float s = 0.f;
