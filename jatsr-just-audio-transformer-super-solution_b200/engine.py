@@ -32,6 +32,42 @@ class PackedWeights:
     def __init__(self, model, device):
         self.device = device
         self.versions = self._versions(model)
+        self._build(model, device)
+        self._map_sources(model)
+
+    def _map_sources(self, model):
+        """(bf16 destination view, parameter) pairs and (f32 destination, parameter) pairs: `refresh` re-casts every
+        parameter into the SAME device buffers with two multi-tensor copies (pointers in `struct` stay valid), instead of
+        re-allocating ~400 tensors after every optimizer step."""
+        k = self.keep
+        D = model.hidden_size
+        attn0 = model.blocks[0].attn
+        qd, kd = attn0.q_proj.out_features, attn0.k_proj.out_features
+        pe, te = model.patch_embed.proj, model.t_embedder
+        pairs = [(k["pe_w1"], pe[0].weight), (k["pe_b1"], pe[0].bias), (k["pe_w2"], pe[2].weight), (k["pe_b2"], pe[2].bias),
+                 (k["te_w1"], te[1].weight), (k["te_b1"], te[1].bias), (k["te_w2"], te[3].weight), (k["te_b2"], te[3].bias),
+                 (k["final_w"], model.final_layer[1].weight), (k["final_b"], model.final_layer[1].bias)]
+        for i, b in enumerate(model.blocks):
+            pairs += [(k["ada_w"][i * 6 * D:(i + 1) * 6 * D], b.adaLN_modulation[1].weight),
+                      (k["ada_b"][i * 6 * D:(i + 1) * 6 * D], b.adaLN_modulation[1].bias),
+                      (k["wqkv"][i][:qd], b.attn.q_proj.weight), (k["wqkv"][i][qd:qd + kd], b.attn.k_proj.weight),
+                      (k["wqkv"][i][qd + kd:], b.attn.v_proj.weight), (k["wo"][i], b.attn.out_proj.weight),
+                      (k["w1"][i], b.mlp[0].weight), (k["b1"][i], b.mlp[0].bias), (k["w2"][i], b.mlp[3].weight),
+                      (k["b2"][i], b.mlp[3].bias)]
+            if "n1" in k:
+                pairs += [(k["n1"][i], b.norm1.weight), (k["n2"][i], b.norm2.weight)]
+        if "nf" in k:
+            pairs.append((k["nf"], model.final_layer[0].weight))
+        self._dst = [d for d, _ in pairs]
+        self._src = [p_ for _, p_ in pairs]
+
+    @torch.no_grad()
+    def refresh(self, model):
+        """Re-cast the (updated) parameters into the existing packed buffers."""
+        torch._foreach_copy_(self._dst, [p_.detach() for p_ in self._src])
+        self.versions = self._versions(model)
+
+    def _build(self, model, device):
         bf = lambda t: t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
         D, depth = model.hidden_size, len(model.blocks)
@@ -151,9 +187,9 @@ class PackedGrads:
         w.final_w, w.final_b = p(k["final_w"]), p(k["final_b"])
 
     def zero_(self):
-        for v in self.keep.values():
-            for t in (v if isinstance(v, list) else [v]):
-                t.zero_()
+        if getattr(self, "_all", None) is None:
+            self._all = [t for v in self.keep.values() for t in (v if isinstance(v, list) else [v])]
+        torch._foreach_zero_(self._all)
 
 
 class TrainBuffers:
@@ -237,8 +273,14 @@ class Engine:
         self.workspaces = {}
 
     def weights(self, device):
-        if self.packed is None or self.packed.stale(self.model, device):
+        if self.packed is None or self.packed.device != device:
             self.packed = PackedWeights(self.model, device)
+        elif self.packed.stale(self.model, device):
+            same_objects = [id(p) for p in self.model.parameters()] == [v[0] for v in self.packed.versions]
+            if same_objects and all(p.device == device for p in self.model.parameters()):
+                self.packed.refresh(self.model)   # same buffers, same pointers: plans and captured graphs stay valid
+            else:
+                self.packed = PackedWeights(self.model, device)
         return self.packed
 
     def workspace(self, B, T, Bt, device, keep_blocks=False):

@@ -58,8 +58,15 @@ class _Stage(torch.autograd.Function):
             by_param = eng.backward_block(ctx.index, B, T, dev)
         else:
             by_param = eng.backward_end(B, T, dev)
-        # fresh tensors: autograd / DDP keep (or accumulate into) what is returned, the packed buffers are reused
-        grads = tuple(by_param[p].clone() if p.requires_grad else None for p in ctx.params)
+        # fresh tensors: autograd / DDP keep (or accumulate into) what is returned, the packed buffers are reused.
+        # One flat allocation + one multi-tensor copy per stage instead of a clone per parameter.
+        need = [p for p in ctx.params if p.requires_grad]
+        flat = torch.empty(sum(p.numel() for p in need), dtype=torch.float32, device=dev)
+        outs = [v.view(p.shape) for v, p in zip(flat.split([p.numel() for p in need]), need)]
+        if outs:
+            torch._foreach_copy_(outs, [by_param[p] for p in need])
+        it = iter(outs)
+        grads = tuple(next(it) if p.requires_grad else None for p in ctx.params)
         tok = None if ctx.kind == "embed" else torch.zeros(1, device=dev)
         return (None, None, None, tok, None) + grads
 
