@@ -357,7 +357,11 @@ def train_main(a, K, W, rank, world, local):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.1, fused=True)   # train_ddp_v3mod2.py:709
+    fused_opt = os.environ.get("JAT_BENCH_TORCH_OPT", "0") == "0"
+    if fused_opt:   # clip_grad_norm_(1.0) + AdamW + bf16 re-pack in two multi-tensor passes (jat_b200.FusedAdamW)
+        opt = jat_b200.FusedAdamW(model.parameters(), lr=5e-5, weight_decay=0.1, max_grad_norm=1.0, model=model)
+    else:           # the reference's own calls, train_ddp_v3mod2.py:709, 926-928
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.1, fused=True)
     gd = torch.Generator(device=dev).manual_seed(100 + rank)
     hr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3                   # raw (un-normalised) DAC latents
     lr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3
@@ -375,8 +379,9 @@ def train_main(a, K, W, rank, world, local):
         opt.zero_grad(set_to_none=True)
         loss = training.mse_loss(net(z_t, t, lr_cond), hr_norm)                       # :886-889, fused with its gradient seed
         loss.backward()                                                               # :922 (+ DDP all-reduce)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                       # :926
-        opt.step()
+        if not fused_opt:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                   # :926
+        opt.step()                                                                    # :928
         return loss
 
     def barrier():
@@ -424,7 +429,8 @@ def train_main(a, K, W, rank, world, local):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "configs[3]: v3mod2 DiT 1280/28/20Q/4KV training step, batch 28 x [1024,1378] per GPU "
                                        "(9660 token rows): normalise + cond-noise + flow-matching mix, forward (Dropout 0.1, DropPath 0.05), "
-                                       "MSE x-prediction loss, backward, clip_grad_norm_, AdamW(fused), bf16 weight re-pack",
+                                       "MSE x-prediction loss, backward, clip_grad_norm_(1.0) + AdamW + bf16 weight re-pack "
+                                       + ("(jat_b200.FusedAdamW: 2 multi-tensor passes)" if fused_opt else "(torch: foreach clip, fused AdamW, re-cast)"),
                            "norm": a.norm, "dropout": cfg["dropout"], "drop_path": cfg["drop_path_rate"],
                            "cond_noise_ratio": 0.05,
                            "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU"},

@@ -340,6 +340,34 @@ int jat_dit_backward_end(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_w
  * out bf16 [B*N, C*P], out[b*N + n, c*P + p] = x[b, c, n*P + p] (0 past T). */
 int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int C, int T, int P, void* stream);
 
+/* ---- parameter update of the training step (replaces torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step of
+ * train_ddp_v3mod2.py:926-928 and the bf16 re-pack of the updated weights; same arithmetic as ATen's fused AdamW) ----
+ * One entry per parameter tensor, all f32 and contiguous; the table lives in DEVICE memory.  `packed` (optional) receives
+ * the updated values as well, in packed_dtype (JAT_DTYPE_BF16 / JAT_DTYPE_F32): the copy the forward GEMMs read.
+ * vec_ok = 1 when every pointer is 16-byte aligned and numel % 4 == 0 (128-bit accesses), else 0 (scalar path).
+ * chunk_first [n_tensors] (device, int32): index of each tensor's first chunk, a chunk being jat_adamw_chunk_elems()
+ * consecutive elements (the last chunk of a tensor may be short); total_chunks = their sum. */
+typedef struct jat_adamw_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    void* packed;
+    int64_t numel;
+    int32_t packed_dtype;
+    int32_t vec_ok;
+} jat_adamw_tensor;
+int jat_adamw_chunk_elems(void);
+/* sumsq_dev[0] (+)= sum over all table entries of grad^2 (f32 per-chunk partials in partials_dev [total_chunks], summed in
+ * chunk order in f64: bit-reproducible).  accumulate != 0 adds to the existing value (several parameter groups). */
+int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
+                   int total_chunks, float* partials_dev, double* sumsq_dev, int accumulate, void* stream);
+/* AdamW (decoupled weight decay, no amsgrad) on every table entry; step counts from 1.  max_norm > 0: the gradients are
+ * scaled by min(1, max_norm / (sqrt(*sumsq_dev) + 1e-6)) on the fly (clip_grad_norm_; `grad` itself is not modified). */
+int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
+                   int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                   float max_norm, const double* sumsq_dev, void* stream);
+
 /* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
 int64_t jat_launch_count(const jat_ctx* ctx);
 
@@ -347,7 +375,10 @@ int64_t jat_launch_count(const jat_ctx* ctx);
 int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
 /* Tail split (default off): when the persistent tile schedule ends in a partial wave, the tiles of that wave are cut
  * along K into parts that fill the machine; the parts park their f32 accumulators in the ctx scratch and the part that
- * arrives last sums them IN PART ORDER and runs the fused epilogue, so results stay bit-reproducible run to run. */
+ * arrives last sums them IN PART ORDER and runs the fused epilogue, so results stay bit-reproducible run to run.
+ * enable == 2: only the reduce-add epilogues (GATE_RESIDUAL / ACCUM without a pre-gate copy) are split and every part
+ * reduce-adds its partial sum straight into the output (bias with part 0): no scratch round trip, but the f32 adds of
+ * one tile's parts land in arrival order, so those tiles may differ in the last bit run to run. */
 int jat_set_gemm_tail_split(jat_ctx* ctx, int enable);
 
 /* Per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline of

@@ -26,6 +26,7 @@ NORM_LAYERNORM, NORM_RMSNORM = 0, 1
 EPI_BIAS_ACT, EPI_QKV_ROPE, EPI_GATE_RESIDUAL, EPI_UNPATCHIFY, EPI_ACCUM, EPI_DACT = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_GELU_ERF, ACT_SILU = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
+ERR_BAD_ARG = -1
 ERR_SEQ_TOO_LONG = -5
 DROP_SITE_ATTN, DROP_SITE_MLP_HIDDEN, DROP_SITE_MLP_OUT, DROP_SITE_PATH = 0, 1, 2, 3
 
@@ -116,6 +117,10 @@ SIGNATURES = {
     "jat_gqa_attention_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u32,
                                            _vp]),
     "jat_gate_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _f, _u32, _vp, _vp]),
+    "jat_adamw_chunk_elems": (_i, []),
+    "jat_grad_sumsq": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "jat_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _f, _vp,
+                            _vp]),
     "jat_abi_version": (_i, []),
     "jat_last_error": (C.c_char_p, []),
     "jat_create": (_i, [_i, C.POINTER(_vp)]),

@@ -2,6 +2,7 @@
 // construction, kernel dispatch, and the host-side launch plan of the whole DiT forward.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <stdio.h>
@@ -18,6 +19,7 @@
 #include "chunks.cuh"
 #include "elementwise.cuh"
 #include "gemm_tcgen05.cuh"
+#include "optimizer.cuh"
 #include "train_step.cuh"
 
 using namespace jat;
@@ -44,7 +46,8 @@ struct jat_ctx {
     // GEMM tail split (see GemmParams): partial-accumulator workspace (one 128x256 f32 tile per SM) + arrival counters
     float* tail_ws;
     int* tail_cnt;
-    int tail_split;        // 1 = cut the tiles of a partial last wave along K
+    int tail_split;        // 0 = off; 1 = cut the tiles of a partial last wave along K, in-order fix-up (any epilogue);
+                           // 2 = the same cut for the reduce-add epilogues only, parts added straight into the output
     long long* gemm_trace; // debug: device buffer of 64 x 8 clock64 slots for the GEMM kernel, or NULL
 };
 static const size_t kTailWsBytesPerSM = 128 * 256 * sizeof(float);
@@ -53,10 +56,10 @@ static const char* const kKernelTags[] = {"gemm_bias_act", "gemm_qkv_rope", "gem
                                           "adaln_norm_modulate", "patchify_cast", "timestep_features",
                                           "cfg_euler_update", "gqa_attention_fwd", "chunk_normalize", "crossfade_denorm",
                                           "gemm_accum", "gemm_dact", "adaln_bwd", "gate_bwd", "colsum_cast", "attention_bwd",
-                                          "train_glue"};
+                                          "train_glue", "optimizer"};
 enum { TAG_GEMM0 = 0, TAG_ADALN = 4, TAG_PATCHIFY = 5, TAG_TSTEP = 6, TAG_EULER = 7, TAG_ATTN = 8, TAG_CHUNKN = 9,
        TAG_XFADE = 10, TAG_GEMM_ACCUM = 11, TAG_GEMM_DACT = 12, TAG_ADALN_BWD = 13,
-       TAG_GATE_BWD = 14, TAG_COLSUM = 15, TAG_ATTN_BWD = 16, TAG_TRAIN_GLUE = 17, TAG_COUNT = 18 };
+       TAG_GATE_BWD = 14, TAG_COLSUM = 15, TAG_ATTN_BWD = 16, TAG_TRAIN_GLUE = 17, TAG_OPTIMIZER = 18, TAG_COUNT = 19 };
 
 static thread_local char g_err[512] = "";
 
@@ -113,7 +116,8 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->att_trace = nullptr;
     c->tail_ws = nullptr;
     c->tail_cnt = nullptr;
-    c->tail_split = 0;
+    c->tail_split = getenv("JAT_GEMM_TAIL") ? atoi(getenv("JAT_GEMM_TAIL")) : 0;
+    if (c->tail_split < 0 || c->tail_split > 2) c->tail_split = 0;
     c->gemm_trace = nullptr;
     const size_t cnt_bytes = (size_t)c->sm_count * GEMM_EPI_WARPS * sizeof(int);
     if (cudaMalloc(&c->tail_ws, kTailWsBytesPerSM * c->sm_count) != cudaSuccess ||
@@ -152,7 +156,7 @@ extern "C" int jat_debug_set_gemm_trace(jat_ctx* ctx, void* buf) {
 
 extern "C" int jat_set_gemm_tail_split(jat_ctx* ctx, int enable) {
     if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
-    ctx->tail_split = enable ? 1 : 0;
+    ctx->tail_split = enable == 2 ? 2 : (enable ? 1 : 0);
     return 0;
 }
 
@@ -474,16 +478,22 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     }
     p.head_tiles = p.num_tiles;
     p.tail_splits = 1;
+    p.tail_direct = 0;
     p.tail_ws = ctx->tail_ws;
     p.tail_cnt = ctx->tail_cnt;
     {
         const int clusters = ctx->sm_count / cg;
         const int rem = p.num_tiles % clusters;
-        if (ctx->tail_split && mc == 1 && p.k_splits == 1 && p.num_tiles > clusters && rem > 0) {
+        // mode 2: reduce-add epilogues without a pre-gate copy only -- every part runs the ordinary epilogue on its
+        // partial sum (bias with part 0), so there is no workspace round trip; the f32 adds of the parts of one tile land
+        // in arrival order (last-bit run-to-run differences in those tiles)
+        const bool direct = ctx->tail_split == 2;
+        const bool direct_ok = (e->kind == JAT_EPI_GATE_RESIDUAL || e->kind == JAT_EPI_ACCUM) && e->aux == nullptr;
+        if (ctx->tail_split && (!direct || direct_ok) && mc == 1 && p.k_splits == 1 && p.num_tiles > clusters && rem > 0) {
             int splits = clusters / rem;
             if (splits > 8) splits = 8;
             if (splits > p.num_k_blocks / 2) splits = p.num_k_blocks / 2;
-            if (splits >= 2) { p.head_tiles = p.num_tiles - rem; p.tail_splits = splits; }
+            if (splits >= 2) { p.head_tiles = p.num_tiles - rem; p.tail_splits = splits; p.tail_direct = direct ? 1 : 0; }
         }
     }
 
@@ -767,6 +777,58 @@ extern "C" int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target
     pre_launch(ctx, TAG_TRAIN_GLUE, s);
     mse_loss_kernel<<<blocks, 256, 0, s>>>(pred, target, d_pred, stats4, (long long)n, (float)(2.0 / (double)n));
     return post_launch(ctx, "mse_loss");
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer step
+static_assert(sizeof(jat_adamw_tensor) == sizeof(OptTensor), "jat_adamw_tensor layout");
+
+extern "C" int jat_adamw_chunk_elems(void) { return OPT_CHUNK; }
+
+static int opt_check(const char* fn, jat_ctx* ctx, const void* table, const void* chunk_first, int n_tensors, int total_chunks) {
+    if (!ctx || !table || !chunk_first) return fail(JAT_ERR_BAD_ARG, "%s: null argument", fn);
+    if (n_tensors <= 0 || total_chunks < n_tensors) return fail(JAT_ERR_BAD_ARG, "%s: bad tensor / chunk count", fn);
+    return 0;
+}
+
+extern "C" int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
+                              int total_chunks, float* partials_dev, double* sumsq_dev, int accumulate, void* stream) {
+    JAT_TRY(opt_check("jat_grad_sumsq", ctx, table_dev, chunk_first_dev, n_tensors, total_chunks));
+    if (!partials_dev || !sumsq_dev) return fail(JAT_ERR_BAD_ARG, "jat_grad_sumsq: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    pre_launch(ctx, TAG_OPTIMIZER, s);
+    grad_sumsq_kernel<<<(unsigned)total_chunks, OPT_THREADS, 0, s>>>((const OptTensor*)table_dev, chunk_first_dev, n_tensors,
+                                                                      partials_dev);
+    JAT_TRY(post_launch(ctx, "grad_sumsq"));
+    pre_launch(ctx, TAG_OPTIMIZER, s);
+    grad_sumsq_final_kernel<<<1, 1024, 0, s>>>(partials_dev, total_chunks, sumsq_dev, accumulate);
+    return post_launch(ctx, "grad_sumsq_final");
+}
+
+extern "C" int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
+                              int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay,
+                              int64_t step, float max_norm, const double* sumsq_dev, void* stream) {
+    JAT_TRY(opt_check("jat_adamw_step", ctx, table_dev, chunk_first_dev, n_tensors, total_chunks));
+    if (step < 1) return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: step counts from 1 (got %lld)", (long long)step);
+    if (!(lr >= 0.0) || !(eps >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(weight_decay >= 0.0))
+        return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: hyper-parameter out of range");
+    if (max_norm > 0.f && !sumsq_dev) return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: clipping needs the gradient sum of squares");
+    AdamWArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    a.bias_corr1 = (float)(1.0 - pow(beta1, (double)step));
+    a.bias_corr2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    a.max_norm = max_norm;
+    a.sumsq = sumsq_dev;
+    a.lr_wd = (float)(lr * weight_decay);
+    a.b1 = (float)beta1; a.one_minus_b1 = (float)(1.0 - beta1);
+    a.b2 = (float)beta2; a.one_minus_b2 = (float)(1.0 - beta2);
+    a.eps_f = (float)eps;
+    a.step_size = (float)(lr / (double)a.bias_corr1);
+    cudaStream_t s = (cudaStream_t)stream;
+    pre_launch(ctx, TAG_OPTIMIZER, s);
+    static const bool f64_math = getenv("JAT_ADAMW_F64") && atoi(getenv("JAT_ADAMW_F64")) != 0;  // ATen's operand types
+    if (f64_math) adamw_kernel<1><<<(unsigned)total_chunks, OPT_THREADS, 0, s>>>((const OptTensor*)table_dev, chunk_first_dev, n_tensors, a);
+    else adamw_kernel<0><<<(unsigned)total_chunks, OPT_THREADS, 0, s>>>((const OptTensor*)table_dev, chunk_first_dev, n_tensors, a);
+    return post_launch(ctx, "adamw");
 }
 
 // ------------------------------------------------------------------------------------------------ chunks

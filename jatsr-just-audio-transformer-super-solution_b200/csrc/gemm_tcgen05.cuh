@@ -52,6 +52,7 @@ struct GemmParams {
     // (x k_splits); each tile in [head_tiles, num_tiles) is cut into tail_splits reduction parts whose f32 partial
     // accumulators go to tail_ws; the part that arrives last (tail_cnt) sums them in part order and runs the epilogue.
     int head_tiles, tail_splits;
+    int tail_direct;  // 1: reduce-add epilogues only -- the parts of a tail tile add their partial sums straight into the output
     float* tail_ws;
     int* tail_cnt;
     long long* trace;  // diagnostics: clock64 timestamps of cluster 0 / CTA rank 0, 8 slots per work item, or NULL
@@ -79,7 +80,7 @@ __device__ __forceinline__ GemmWork gemm_decode_work(const GemmParams& p, int wo
         const int w2 = work - head_items;
         const int t2 = w2 / p.tail_splits;
         w.tile = p.head_tiles + t2; w.part = w2 - t2 * p.tail_splits; parts = p.tail_splits;
-        w.tail = p.tail_splits > 1 ? t2 : -1;
+        w.tail = (p.tail_splits > 1 && !p.tail_direct) ? t2 : -1;
     }
     if (parts == 1) { w.kb0 = 0; w.kb1 = p.num_k_blocks; }
     else { w.kb0 = p.num_k_blocks * w.part / parts; w.kb1 = p.num_k_blocks * (w.part + 1) / parts; }

@@ -32,6 +32,10 @@ class PackedWeights:
     def __init__(self, model, device):
         self.device = device
         self.versions = self._versions(model)
+        # True once a backward pass has produced gradients from these copies: an optimizer step probably follows, and not
+        # every in-place update bumps `Tensor._version` (torch's fused AdamW / `p.data` writes do not), so the next
+        # forward re-casts unless the updater (jat_b200.FusedAdamW) has written the copies itself and cleared the flag
+        self.dirty = False
         self._build(model, device)
         self._map_sources(model)
 
@@ -66,6 +70,7 @@ class PackedWeights:
         """Re-cast the (updated) parameters into the existing packed buffers."""
         torch._foreach_copy_(self._dst, [p_.detach() for p_ in self._src])
         self.versions = self._versions(model)
+        self.dirty = False
 
     def _build(self, model, device):
         bf = lambda t: t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
@@ -275,7 +280,7 @@ class Engine:
     def weights(self, device):
         if self.packed is None or self.packed.device != device:
             self.packed = PackedWeights(self.model, device)
-        elif self.packed.stale(self.model, device):
+        elif self.packed.dirty or self.packed.stale(self.model, device):
             same_objects = [id(p) for p in self.model.parameters()] == [v[0] for v in self.packed.versions]
             if same_objects and all(p.device == device for p in self.model.parameters()):
                 self.packed.refresh(self.model)   # same buffers, same pointers: plans and captured graphs stay valid
@@ -354,7 +359,10 @@ class Engine:
         return out
 
     def _bwd_args(self, dev, B, T):
-        pw, ws, tb = self.weights(dev), self.workspace(B, T, B, dev), self.train_buffers(B, T, dev)
+        pw, ws, tb = self.packed, self.workspace(B, T, B, dev), self.train_buffers(B, T, dev)  # the forward's copies, as they are
+        if pw is None or pw.device != dev:
+            raise L.JatError(L.ERR_BAD_ARG, "backward without a matching forward_train on this device")
+        pw.dirty = True
         gr = self.grads(dev)
         return (L.context(self._dev_index(dev)), C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), C.byref(tb.sc),
                 C.byref(gr.struct)), gr

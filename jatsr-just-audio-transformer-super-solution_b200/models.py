@@ -224,6 +224,13 @@ class _JaTBase(nn.Module):
         return self._engine.forward(x_t.float().contiguous(), t.float().contiguous(), x_cond.float().contiguous(),
                                     keep_blocks=True)
 
+    def refresh_packed_weights(self):
+        """Re-cast the parameters into the packed device copies before the next forward.  Needed only after in-place
+        writes that autograd's version counters do not see and that were not followed by a backward pass (e.g.
+        `p.data.copy_(...)` from an EMA shadow); optimizer steps, `load_state_dict` and `.to()` are detected."""
+        if self._engine.packed is not None:
+            self._engine.packed.dirty = True
+
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         if getattr(self, "_engine", None) is not None:

@@ -105,11 +105,12 @@ def gemm(A, W, *, kind=L.EPI_BIAS_ACT, act=L.ACT_NONE, out_dtype=L.DTYPE_BF16, b
     return out
 
 
-def set_gemm_tail_split(device, enable):
-    """Toggle the GEMM tail split (deterministic split-K fix-up of a partial last wave) on a device's context."""
+def set_gemm_tail_split(device, mode):
+    """GEMM tail split on a device's context: 0 / False = off, 1 / True = deterministic split-K fix-up of a partial last
+    wave (any epilogue), 2 = reduce-add epilogues only, parts added straight into the output (no workspace round trip)."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    L.check(L.load().jat_set_gemm_tail_split(L.context(idx), int(bool(enable))))
+    L.check(L.load().jat_set_gemm_tail_split(L.context(idx), int(mode)))
 
 
 def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None, drop_p=0.0, drop_seed=0):

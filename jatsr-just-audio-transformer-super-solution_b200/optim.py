@@ -1,0 +1,172 @@
+"""The parameter update of the training step as two multi-tensor CUDA passes (optimizer side).
+
+  FusedAdamW  <->  train_ddp_v3mod2.py:709 `optim.AdamW(model.parameters(), lr, weight_decay)` together with
+                   :926 `clip_grad_norm_(model.parameters(), 1.0)` and the re-cast of the updated f32 parameters into
+                   the packed bf16 buffers the GEMMs read (engine.PackedWeights.refresh).
+
+It IS a `torch.optim.AdamW`: same constructor, same `param_groups` (lr schedulers work), same `state` / `state_dict()`
+layout (`step`, `exp_avg`, `exp_avg_sq` per parameter), so the reference's checkpoints load into it and its checkpoints
+load into the stock optimizer.  Only `step()` differs: `jat_grad_sumsq` (one read of the gradients -> ||g||^2 on the
+device) and `jat_adamw_step` (one pass: clip coefficient applied on the fly, decoupled decay, Adam update with ATen's
+operand types, packed copy written in the same pass).  There is no host synchronisation and no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .ops import _stream
+
+
+class _Group:
+    """Device table (jat_adamw_tensor [n]) + chunk index of one parameter group."""
+
+    def __init__(self, params, states, packed_of, device):
+        self.params = params
+        self.ids = [id(p) for p in params]
+        n = len(params)
+        chunk = L.load().jat_adamw_chunk_elems()
+        first, total = [], 0
+        for p in params:
+            first.append(total)
+            total += (p.numel() + chunk - 1) // chunk
+        self.n, self.total_chunks = n, total
+        self.chunk_first = torch.tensor(first, dtype=torch.int32).to(device)
+        self.table = torch.zeros(n, 7, dtype=torch.int64, device=device)
+        self.partials = torch.empty(total, dtype=torch.float32, device=device)
+        dsts = [packed_of.get(id(p)) for p in params]
+        rows = [[p.data_ptr(), 0, states[p]["exp_avg"].data_ptr(), states[p]["exp_avg_sq"].data_ptr(),
+                 d.data_ptr() if d is not None else 0, p.numel(), 0] for p, d in zip(params, dsts)]
+        self.static = torch.tensor(rows, dtype=torch.int64)
+        self.static_ok = torch.tensor([all(r[j] % 16 == 0 for j in (0, 2, 3, 4)) and r[5] % 4 == 0 for r in rows])
+        self.dtype_bits = torch.tensor([1 if (d is not None and d.dtype == torch.bfloat16) else 0 for d in dsts],
+                                       dtype=torch.int64)
+        self.key = self._key(states)
+
+    def _key(self, states):
+        return tuple((p.data_ptr(), states[p]["exp_avg"].data_ptr(), states[p]["exp_avg_sq"].data_ptr()) for p in self.params)
+
+    def upload(self):
+        """Gradient pointers change from step to step (autograd hands out fresh tensors): column 1 + the vec_ok flag.
+        A fresh pageable host tensor per step: the driver stages it at call time, so the host may run ahead of the stream."""
+        g = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
+        h = self.static.clone()
+        h[:, 1] = g
+        h[:, 6] = self.dtype_bits | ((self.static_ok & (g % 16 == 0)).to(torch.int64) << 32)
+        self.table.copy_(h, non_blocking=True)
+
+
+class FusedAdamW(torch.optim.AdamW):
+    """`torch.optim.AdamW` whose `step()` runs on the library's multi-tensor kernels.
+
+    max_grad_norm: if set, `step()` also does what `clip_grad_norm_(params, max_grad_norm)` does before the update (one
+        norm over ALL parameters of the optimizer), except that `p.grad` is left unscaled; the total norm of the last
+        step is in `self.grad_norm` (device scalar, no sync).
+    model: a jat_b200 drop-in module; its packed bf16 / f32 weight copies are then refreshed by the same pass, so the next
+        forward does not re-cast 766 M parameters.
+    Every parameter must be f32, contiguous, on one CUDA device and have a dense gradient at `step()` time."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, *, max_grad_norm=None, model=None):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False, fused=False)
+        self.max_grad_norm = None if max_grad_norm is None else float(max_grad_norm)
+        self._model = model
+        self._groups = None
+        self._packed_seen = None
+        self._sumsq = None
+        self._covers_model = False
+        self.grad_norm = None
+
+    # state in torch.optim.AdamW's layout (torch/optim/adam.py:_init_group): step (f32 scalar), exp_avg, exp_avg_sq
+    def _ensure_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _packed_map(self):
+        eng = getattr(self._model, "_engine", None) if self._model is not None else None
+        pk = eng.packed if eng is not None else None
+        if pk is None:
+            return None, {}
+        return pk, {id(src): dst for dst, src in zip(pk._dst, pk._src)}
+
+    def _build(self, device):
+        pk, packed_of = self._packed_map()
+        self._packed_seen = pk
+        self._groups = []
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.grad is not None]
+            for p in params:
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.device != device or p.grad.is_sparse:
+                    raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: parameters must be f32, contiguous, dense and on one CUDA device")
+                self._ensure_state(p)
+                if self.state[p]["exp_avg"].device != device:  # state loaded from a checkpoint on another device
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        self.state[p][k] = self.state[p][k].to(device)
+            self._groups.append(_Group(params, self.state, packed_of, device) if params else None)
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=device)
+        # the packed copies may be declared fresh after a step only if this optimizer updates every parameter they mirror
+        mine = {id(p) for g in self._groups if g is not None for p in g.params}
+        self._covers_model = pk is not None and all(id(src) in mine for src in pk._src) and \
+            all(id(p) in packed_of for p in self._model.parameters())
+
+    def _current(self):
+        if self._groups is None:
+            return False
+        pk, _ = self._packed_map()
+        if pk is not self._packed_seen:
+            return False
+        for group, g in zip(self.param_groups, self._groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if (g is None) != (not params) or (g is not None and ([id(p) for p in params] != g.ids or g.key != g._key(self.state))):
+                return False
+        return True
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        first = next((p for group in self.param_groups for p in group["params"] if p.grad is not None), None)
+        if first is None:
+            return loss
+        device = first.device
+        if device.type != "cuda":
+            raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW runs on CUDA parameters only (no CPU path)")
+        if not self._current():
+            self._build(device)
+        lib, ctx, stream = L.load(), L.context(device.index if device.index is not None else torch.cuda.current_device()), \
+            _stream(device)
+        live = [g for g in self._groups if g is not None]
+        for g in live:
+            g.upload()
+        clip = self.max_grad_norm is not None
+        if clip:
+            for j, g in enumerate(live):
+                L.check(lib.jat_grad_sumsq(ctx, g.table.data_ptr(), g.chunk_first.data_ptr(), g.n, g.total_chunks,
+                                           g.partials.data_ptr(), self._sumsq.data_ptr(), int(j > 0), stream))
+            self.grad_norm = self._sumsq.sqrt().float().squeeze(0)
+        for group, g in zip(self.param_groups, self._groups):
+            if g is None:
+                continue
+            if group.get("amsgrad") or group.get("maximize"):
+                raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: amsgrad / maximize are not supported")
+            steps = [self.state[p]["step"] for p in g.params]
+            torch._foreach_add_(steps, 1)
+            step = int(steps[0].item())   # host tensor: no device sync
+            b1, b2 = group["betas"]
+            lr = group["lr"]
+            L.check(lib.jat_adamw_step(ctx, g.table.data_ptr(), g.chunk_first.data_ptr(), g.n, g.total_chunks,
+                                       float(lr), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                       step, float(self.max_grad_norm) if clip else 0.0,
+                                       self._sumsq.data_ptr() if clip else None, stream))
+        # the kernels wrote through raw pointers: tell autograd / the engine that the parameters changed ...
+        torch.autograd.graph.increment_version([p for g in live for p in g.params])
+        pk = self._packed_seen
+        if pk is not None and self._covers_model:
+            pk.versions = pk._versions(self._model)   # ... and that the packed copies already hold the new values
+            pk.dirty = False
+        return loss

@@ -108,3 +108,21 @@ def test_state_dict_is_interchangeable_with_reference(cls_name):
     ours.load_state_dict(a, strict=True)
     ref.load_state_dict(b, strict=True)
     assert [n for n, _ in ref.named_parameters()] == [n for n, _ in ours.named_parameters()]
+
+
+def test_fused_adamw_is_a_torch_adamw_and_has_no_cpu_path(lib):
+    """Same constructor / param_groups / state_dict layout as torch.optim.AdamW (train_ddp_v3mod2.py:709); stepping CPU
+    parameters raises instead of falling back."""
+    import jat_b200
+    m = torch.nn.Linear(4, 3)
+    stock = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.1)
+    m(torch.randn(2, 4)).sum().backward()
+    stock.step()
+    opt = jat_b200.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, max_grad_norm=1.0, model=None)
+    assert isinstance(opt, torch.optim.AdamW)
+    opt.load_state_dict(stock.state_dict())
+    sd = opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 1.0
+    assert set(sd["param_groups"][0]) == set(stock.state_dict()["param_groups"][0])
+    with pytest.raises(lib.JatError):
+        opt.step()

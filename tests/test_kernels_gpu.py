@@ -300,6 +300,42 @@ def test_gemm_tail_split_matches_unsplit_and_is_deterministic(ops, L, cta_pair, 
         assert rel_l2(split[lo:], want) < 1e-4
 
 
+@pytest.mark.parametrize("cta_pair,block_n", GEMM_CFGS)
+@pytest.mark.parametrize("N,K", [(1280, 1280), (1280, 5120)])
+def test_gemm_tail_split_direct_gate_residual(ops, L, cta_pair, block_n, N, K):
+    """Tail split mode 2 (out_proj / fc2 shapes of the headline step): the parts of a tail tile reduce-add their partial
+    sums straight into the residual stream (bias with part 0).  Same result as the unsplit schedule up to f32 summation
+    order; other epilogues are left unsplit in this mode (bit-identical to mode 0)."""
+    B, Ntok = 56, 345
+    M = B * Ntok
+    A, W, bias = _ab(M, N, K, seed=12)
+    gate = torch.randn(B, N, device=dev())
+    x0 = torch.randn(M, N, device=dev())
+
+    def run():
+        x = x0.clone()
+        ops.gemm(A, W, kind=L.EPI_GATE_RESIDUAL, out=x, bias=bias, gate=gate, gate_batch_stride=N, tokens_per_batch=Ntok,
+                 cta_pair=cta_pair, block_n=block_n)
+        return x
+    try:
+        ops.set_gemm_tail_split(dev(), 0)
+        plain = run()
+        plain_bf16 = ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, cta_pair=cta_pair, block_n=block_n)
+        ops.set_gemm_tail_split(dev(), 2)
+        split = run()
+        split_bf16 = ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, cta_pair=cta_pair, block_n=block_n)
+    finally:
+        ops.set_gemm_tail_split(dev(), 0)
+    assert torch.equal(split_bf16, plain_bf16)
+    assert rel_l2(split, plain) < 2e-6
+    lo = M - 700
+    y = A[lo:].float() @ W.float().t() + bias
+    want = x0[lo:] + gate.repeat_interleave(Ntok, 0)[lo:] * y
+    assert rel_l2(split[lo:], want) < 1e-4
+    head = slice(0, 256 * 60)  # whole tiles of the full waves: untouched by the split
+    assert torch.equal(split[head], plain[head])
+
+
 @pytest.mark.parametrize("kind", ["bias_f32", "bias_gelu_bf16", "qkv_rope", "gate_residual", "unpatchify"])
 @pytest.mark.parametrize("M", [19320, 9660])
 def test_gemm_multicast_cluster_is_bit_identical(ops, L, kind, M):

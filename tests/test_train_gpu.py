@@ -59,10 +59,13 @@ def test_training_step_gradients_match_reference(tag, cls):
     assert worst[1] <= 2 * yard["max_param_rel_l2"], worst
 
 
-def test_training_step_runs_under_optimizer_and_is_repeatable():
+@pytest.mark.parametrize("opt_kind", ["torch_default", "torch_fused", "jat_fused"])
+def test_training_step_runs_under_optimizer_and_is_repeatable(opt_kind):
     """AdamW + clip_grad_norm_ on the drop-in module (train_ddp_v3mod2.py:709,926-929): two identical steps from the same
     state give identical gradients (the backward is deterministic apart from f32 atomics in the column reductions),
-    the loss goes down over a few steps, and eval-mode outputs track the updated parameters (packed weights refreshed)."""
+    the loss goes down over a few steps, and eval-mode outputs track the updated parameters (packed weights refreshed).
+    torch's fused AdamW updates the parameters WITHOUT bumping their version counters: the packed copies must follow
+    all the same (they are re-cast after every backward unless jat_b200.FusedAdamW has already written them)."""
     import jat_b200
     cfg = dict(input_channels=32, cond_channels=32, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
                bottleneck_dim=128, mlp_ratio=2.0, dropout=0.0, drop_path_rate=0.0)
@@ -77,7 +80,10 @@ def test_training_step_runs_under_optimizer_and_is_repeatable():
     hr, lr, eps = (torch.randn(B, 32, T, generator=g, device=dev()) for _ in range(3))
     t = torch.rand(B, generator=g, device=dev())
     z_t = t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * eps
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=0.1)
+    if opt_kind == "jat_fused":
+        opt = jat_b200.FusedAdamW(model.parameters(), lr=2e-3, weight_decay=0.1, max_grad_norm=1.0, model=model)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=0.1, fused=(opt_kind == "torch_fused"))
 
     def grads():
         opt.zero_grad(set_to_none=True)
@@ -89,7 +95,8 @@ def test_training_step_runs_under_optimizer_and_is_repeatable():
     assert l0 == l0b and rel_l2(g0.cpu().numpy(), g0b.cpu().numpy()) < 1e-5
     losses = [l0]
     for _ in range(8):
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if opt_kind != "jat_fused":
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         losses.append(grads()[0])
     assert losses[-1] < 0.9 * losses[0], losses
