@@ -296,6 +296,11 @@ typedef struct jat_dit_saved {
     uint64_t seed;                 /* step seed: every (block, site) mask derives from it */
     const float* drop_path_rates;  /* DEVICE f32 [depth] DropPath.drop_prob per block, or NULL = no DropPath */
     float* dp_scale;               /* f32 [depth, 2, B] per-sample DropPath factors (written by the forward) */
+    /* row statistics (mean, rstd) of norm1 / norm2 per block, f32 [depth, M, 2], written by the forward's norm kernels;
+     * with both given, the block backward runs the fused norm + gate backward kernel (jat_adaln_gate_bwd); NULL = the
+     * backward recomputes them (jat_adaln_bwd + jat_gate_bwd) */
+    float* rs1;
+    float* rs2;
 } jat_dit_saved;
 
 typedef struct jat_dit_bwd_scratch {
@@ -387,6 +392,18 @@ int jat_set_gemm_tail_split(jat_ctx* ctx, int enable);
  * and the launch count.  Not for use during CUDA-graph capture. Returns the number of classes filled. */
 int jat_profile_begin(jat_ctx* ctx);
 int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* total_ms, int64_t* counts);
+
+/* Fused form of jat_adaln_bwd (accumulate = 1, modulated) and the jat_gate_bwd[_dropout] that follows it in the block
+ * backward, for callers that kept the row statistics of the forward norm: rowstats f32 [M, 2] = (mean, rstd) per token row
+ * (what jat_dit_forward_train writes to jat_dit_saved.rs1 / rs2).  One pass over dh, x and dx: dx += norm backward,
+ * dshift / dscale (/ dweight) += column sums; and, when y_bf16 != NULL, on the updated dx row: dy = dropout-mask(dx) *
+ * gate_b * rowscale_b (bf16), dgate_b += rowscale_b * sum_n dx * y, dbias (optional, needs dxsum_scratch f32 [B, D]).
+ * scale and gate share mod_batch_stride; dshift / dscale / dgate share dmod_batch_stride. */
+int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* rowstats, const float* scale,
+                       int64_t mod_batch_stride, const float* weight, int norm_kind, float* dx, float* dshift, float* dscale,
+                       int64_t dmod_batch_stride, float* dweight, const void* y_bf16, const float* gate, void* dy_bf16,
+                       float* dgate, float* dxsum_scratch, float* dbias, int B, int tokens_per_batch, int D, float drop_p,
+                       uint32_t drop_seed, const float* gate_rowscale, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Backward pass of the DiT block (training step: train_ddp_v3mod2.py:886-922 differentiates

@@ -97,7 +97,7 @@ class DitSaved(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x_in", "x_mid", "h1", "qkv", "attn", "lse", "y1", "h2", "u", "mact", "y2",
                                           "pe_u", "t_u1", "t_u2")] + [
         ("dropout_p", C.c_float), ("reserved", C.c_int32), ("seed", C.c_uint64),
-        ("drop_path_rates", C.c_void_p), ("dp_scale", C.c_void_p)]
+        ("drop_path_rates", C.c_void_p), ("dp_scale", C.c_void_p), ("rs1", C.c_void_p), ("rs2", C.c_void_p)]
 
 
 class DitBwdScratch(C.Structure):
@@ -140,6 +140,8 @@ SIGNATURES = {
     "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_gqa_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_cfg_euler_update": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i64, _vp]),
+    "jat_adaln_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _i, _i, _i, _f, _u32, _vp, _vp]),
     "jat_adaln_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _vp, _i, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "jat_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "jat_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),

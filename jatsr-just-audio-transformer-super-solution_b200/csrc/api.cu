@@ -555,13 +555,15 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
 // ------------------------------------------------------------------------------------------------ AdaLN
 template <int NORM>
 static int launch_adaln(jat_ctx* ctx, const float* x, __nv_bfloat16* out, const float* shift, const float* scale,
-                        long long bstride, const float* weight, float eps, int M, int D, int ntok, cudaStream_t s) {
+                        long long bstride, const float* weight, float eps, int M, int D, int ntok, cudaStream_t s,
+                        float2* rowstats = nullptr, float* x_copy = nullptr) {
     const int nvec = D / 4;
     const int nv = (nvec + 31) / 32;
     dim3 grid((M + ADALN_WARPS - 1) / ADALN_WARPS), block(ADALN_WARPS * 32);
     pre_launch(ctx, TAG_ADALN, s);
 #define JAT_ADALN_CASE(NV) \
-    launch_pdl(adaln_norm_modulate_kernel<NV, NORM>, grid, block, 0, s, x, out, shift, scale, bstride, weight, eps, M, D, ntok)
+    launch_pdl(adaln_norm_modulate_kernel<NV, NORM>, grid, block, 0, s, x, out, shift, scale, bstride, weight, eps, M, D, ntok, \
+               rowstats, x_copy)
     if (nv <= 4) JAT_ADALN_CASE(4);
     else if (nv <= 8) JAT_ADALN_CASE(8);
     else if (nv <= 10) JAT_ADALN_CASE(10);
@@ -571,9 +573,21 @@ static int launch_adaln(jat_ctx* ctx, const float* x, __nv_bfloat16* out, const 
     return post_launch(ctx, "adaln_norm_modulate");
 }
 
+static int adaln_norm_modulate_stats(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift, const float* scale,
+                                     int64_t mod_batch_stride, const float* weight, int norm_kind, float eps, int M, int D,
+                                     int tokens_per_batch, float* rowstats, float* x_copy, void* stream);
+
 extern "C" int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift,
                                        const float* scale, int64_t mod_batch_stride, const float* weight, int norm_kind,
                                        float eps, int M, int D, int tokens_per_batch, void* stream) {
+    return adaln_norm_modulate_stats(ctx, x, out_bf16, shift, scale, mod_batch_stride, weight, norm_kind, eps, M, D,
+                                     tokens_per_batch, nullptr, nullptr, stream);
+}
+
+// training forward: rowstats = optional f32 [M, 2] (row mean, rstd), x_copy = optional f32 [M, D] copy of x, both for the backward
+static int adaln_norm_modulate_stats(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift, const float* scale,
+                                     int64_t mod_batch_stride, const float* weight, int norm_kind, float eps, int M, int D,
+                                     int tokens_per_batch, float* rowstats, float* x_copy, void* stream) {
     if (!ctx || !x || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: null argument");
     if ((shift == nullptr) != (scale == nullptr))
         return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: shift and scale must both be given or both NULL");
@@ -584,11 +598,11 @@ extern "C" int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_b
     cudaStream_t s = (cudaStream_t)stream;
     if (norm_kind == JAT_NORM_LAYERNORM)
         return launch_adaln<0>(ctx, x, (__nv_bfloat16*)out_bf16, shift, scale, mod_batch_stride, nullptr, eps, M, D,
-                               tokens_per_batch, s);
+                               tokens_per_batch, s, (float2*)rowstats, x_copy);
     if (norm_kind == JAT_NORM_RMSNORM) {
         if (!weight) return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: RMSNorm needs a weight");
         return launch_adaln<1>(ctx, x, (__nv_bfloat16*)out_bf16, shift, scale, mod_batch_stride, weight, eps, M, D,
-                               tokens_per_batch, s);
+                               tokens_per_batch, s, (float2*)rowstats, x_copy);
     }
     return fail(JAT_ERR_BAD_ARG, "jat_adaln_norm_modulate: unknown norm_kind %d", norm_kind);
 }
@@ -715,6 +729,61 @@ extern "C" int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y
     gate_bwd_kernel<<<grid, block, 0, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride, (__nv_bfloat16*)dy_bf16,
                                            dgate, dmod_batch_stride, xs, D, tokens_per_batch, drop, gate_rowscale);
     JAT_TRY(post_launch(ctx, "gate_bwd"));
+    if (dbias) {
+        pre_launch(ctx, TAG_GATE_BWD, s);
+        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D, gate_rowscale);
+        return post_launch(ctx, "gate_bias_grad");
+    }
+    return 0;
+}
+
+extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* rowstats, const float* scale,
+                                  int64_t mod_batch_stride, const float* weight, int norm_kind, float* dx, float* dshift,
+                                  float* dscale, int64_t dmod_batch_stride, float* dweight, const void* y_bf16,
+                                  const float* gate, void* dy_bf16, float* dgate, float* dxsum_scratch, float* dbias, int B,
+                                  int tokens_per_batch, int D, float drop_p, uint32_t drop_seed, const float* gate_rowscale,
+                                  void* stream) {
+    if (!ctx || !dh_bf16 || !x || !rowstats || !scale || !dx || !dshift || !dscale)
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: null argument");
+    const bool has_gate = y_bf16 != nullptr;
+    if (has_gate && (!gate || !dy_bf16 || !dgate)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: gate / dy / dgate missing");
+    if (dbias != nullptr && (!has_gate || dxsum_scratch == nullptr))
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: dbias needs the gate part and the [B, D] scratch");
+    if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_adaln_gate_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
+    if (mod_batch_stride % 4 != 0 || dmod_batch_stride % 4 != 0)
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: strides %% 4 != 0");
+    if (norm_kind != JAT_NORM_LAYERNORM && norm_kind != JAT_NORM_RMSNORM)
+        return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: unknown norm_kind %d", norm_kind);
+    if (norm_kind == JAT_NORM_RMSNORM && !weight) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: RMSNorm needs a weight");
+    DropCfg drop;
+    if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: drop_p must be in [0, 1)");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* xs = dbias ? dxsum_scratch : nullptr;
+    if (xs) JAT_CUDA(cudaMemsetAsync(xs, 0, (size_t)B * D * sizeof(float), s));
+    // one wave: two CTAs of D/4 threads per SM, every batch item cut into the same number of row ranges
+    int per_batch = (2 * ctx->sm_count) / B;
+    if (per_batch < 1) per_batch = 1;
+    int rows = (tokens_per_batch + per_batch - 1) / per_batch;
+    rows = (rows + AGB_ROWS - 1) / AGB_ROWS * AGB_ROWS;
+    dim3 grid((tokens_per_batch + rows - 1) / rows, B), block((D / 4 + 31) / 32 * 32);
+    const float2* rsp = (const float2*)rowstats;
+    const __nv_bfloat16 *dh = (const __nv_bfloat16*)dh_bf16, *y = (const __nv_bfloat16*)y_bf16;
+    __nv_bfloat16* dy = (__nv_bfloat16*)dy_bf16;
+    pre_launch(ctx, TAG_ADALN_BWD, s);
+#define JAT_AGB(NORM, GATE)                                                                                              \
+    do {                                                                                                                 \
+        if (block.x <= 320)                                                                                              \
+            adaln_gate_bwd_kernel<NORM, GATE, 320><<<grid, block, 0, s>>>(dh, x, rsp, scale, mod_batch_stride, weight, dx, dshift, \
+                dscale, dmod_batch_stride, dweight, y, gate, dy, dgate, xs, drop, gate_rowscale, D, tokens_per_batch, rows); \
+        else                                                                                                             \
+            adaln_gate_bwd_kernel<NORM, GATE, 512><<<grid, block, 0, s>>>(dh, x, rsp, scale, mod_batch_stride, weight, dx, dshift, \
+                dscale, dmod_batch_stride, dweight, y, gate, dy, dgate, xs, drop, gate_rowscale, D, tokens_per_batch, rows); \
+    } while (0)
+    if (norm_kind == JAT_NORM_LAYERNORM) { if (has_gate) JAT_AGB(0, 1); else JAT_AGB(0, 0); }
+    else { if (has_gate) JAT_AGB(1, 1); else JAT_AGB(1, 0); }
+#undef JAT_AGB
+    JAT_TRY(post_launch(ctx, "adaln_gate_bwd"));
     if (dbias) {
         pre_launch(ctx, TAG_GATE_BWD, s);
         gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D, gate_rowscale);
@@ -1155,9 +1224,10 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
         void* attn = at(sv->attn, i, MD, 2);
         void* h2 = at(sv->h2, i, MD, 2);
         void* mact = at(sv->mact, i, (int64_t)M * F, 2);
-        JAT_CUDA(cudaMemcpyAsync(at(sv->x_in, i, MD, 4), ws->x, MD * 4, cudaMemcpyDeviceToDevice, s));
-        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, h1, m, m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind,
-                                        w->norm_eps, M, D, N, stream));
+        // the norm kernel also keeps x (f32) and the row statistics for the backward pass
+        JAT_TRY(adaln_norm_modulate_stats(ctx, ws->x, h1, m, m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind,
+                                          w->norm_eps, M, D, N, sv->rs1 ? sv->rs1 + (int64_t)i * M * 2 : nullptr,
+                                          (float*)at(sv->x_in, i, MD, 4), stream));
         memset(&e, 0, sizeof(e));
         e.kind = JAT_EPI_QKV_ROPE; e.out = qkv; e.ldo = QKV; e.tokens_per_batch = N;
         e.rope_cos = w->rope_cos; e.rope_sin = w->rope_sin; e.rope_cols = (Hq + Hkv) * 64;
@@ -1171,9 +1241,9 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
         e.gate_rowscale = dps ? dps + (int64_t)(2 * i) * B : nullptr;
         JAT_TRY(jat_gemm_bf16(ctx, attn, D, w->wo[i], D, M, D, D, &e, -1, 0, stream));
 
-        JAT_CUDA(cudaMemcpyAsync(at(sv->x_mid, i, MD, 4), ws->x, MD * 4, cudaMemcpyDeviceToDevice, s));
-        JAT_TRY(jat_adaln_norm_modulate(ctx, ws->x, h2, m + 3 * D, m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
-                                        w->norm_kind, w->norm_eps, M, D, N, stream));
+        JAT_TRY(adaln_norm_modulate_stats(ctx, ws->x, h2, m + 3 * D, m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
+                                          w->norm_kind, w->norm_eps, M, D, N, sv->rs2 ? sv->rs2 + (int64_t)i * M * 2 : nullptr,
+                                          (float*)at(sv->x_mid, i, MD, 4), stream));
         e = epi_bias_act(w->b1[i], mact, F, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
         e.aux = at(sv->u, i, (int64_t)M * F, 2); e.ld_aux = F;
         e.drop_p = pd; e.drop_seed = jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_HIDDEN);
@@ -1286,12 +1356,21 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
     JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
     JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    const bool fused = sv->rs1 != nullptr && sv->rs2 != nullptr;
+    if (fused) {
+        // norm2 backward + the gate backward of the attention branch below it (x1 = x + drop_path(gate_msa * (attn(h1) Wo^T)))
+        JAT_TRY(jat_adaln_gate_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), sv->rs2 + (int64_t)i * M * 2, m + 4 * D, NM,
+                                   w->norm2_w ? w->norm2_w[i] : nullptr, w->norm_kind, sc->dx, dm + 3 * D, dm + 4 * D, d.SIXD,
+                                   rms ? (float*)gr->norm2_w[i] : nullptr, at(sv->y1, i, MD, 2), m + 2 * D, sc->dy, dm + 2 * D,
+                                   nullptr, nullptr, B, N, D, 0.0f, 0u, dps ? dps + (int64_t)(2 * i) * B : nullptr, stream));
+    } else {
     JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), m + 4 * D, NM, w->norm2_w ? w->norm2_w[i] : nullptr,
                           w->norm_kind, w->norm_eps, sc->dx, 1, dm + 3 * D, dm + 4 * D, d.SIXD,
                           rms ? (float*)gr->norm2_w[i] : nullptr, sc->rowstats, B, N, D, stream));
     // ---- attention branch: x1 = x + drop_path(gate_msa * (attn(h1) Wo^T))
     JAT_TRY(jat_gate_bwd_dropout(ctx, sc->dx, at(sv->y1, i, MD, 2), m + 2 * D, NM, sc->dy, dm + 2 * D, d.SIXD, nullptr, nullptr,
                                  B, N, D, 0.0f, 0u, dps ? dps + (int64_t)(2 * i) * B : nullptr, stream));
+    }
     JAT_TRY(wgrad(ctx, sc->dy, D, attn, D, (float*)gr->wo[i], D, D, M, stream));
     JAT_TRY(dgrad(ctx, sc->dy, D, w->wo[i], D, D, M, sc->da, JAT_ACT_NONE, nullptr, stream));
     JAT_TRY(jat_gqa_attention_bwd_dropout(ctx, qkv, sc->da, attn, (const float*)at(sv->lse, i, (int64_t)B * d.Hq * N, 4), sc->dsum,
@@ -1299,6 +1378,12 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
                                           jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
     JAT_TRY(wgrad(ctx, sc->dqkv, d.QKV, h1, D, (float*)gr->wqkv[i], d.QKV, D, M, stream));
     JAT_TRY(dgrad(ctx, sc->dqkv, d.QKV, w->wqkv[i], D, d.QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
+    if (fused)
+        JAT_TRY(jat_adaln_gate_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), sv->rs1 + (int64_t)i * M * 2, m + D, NM,
+                                   w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind, sc->dx, dm, dm + D, d.SIXD,
+                                   rms ? (float*)gr->norm1_w[i] : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B,
+                                   N, D, 0.0f, 0u, nullptr, stream));
+    else
     JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,
                           w->norm_kind, w->norm_eps, sc->dx, 1, dm, dm + D, d.SIXD, rms ? (float*)gr->norm1_w[i] : nullptr,
                           sc->rowstats, B, N, D, stream));

@@ -229,6 +229,152 @@ __global__ void gate_bias_grad_kernel(const float* __restrict__ gate, long long 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused AdaLN backward (+ the gate backward that follows it).  In the block backward every adaln_bwd is followed by the
+// gate_bwd of the branch below it, which re-reads the dx row adaln_bwd has just written; and adaln_bwd itself is two
+// kernels (row reductions / column reductions) that both read dh and x.  With the row statistics (mean, rstd) kept by the
+// forward's norm kernel, ONE kernel in the column mapping does all of it: thread = 4 fixed columns, a CTA walks over rows of
+// one batch item in groups of 4; the only cross-thread step is the block reduction of (sum g, sum g xhat) per row
+// (warp shuffles + one __syncthreads per group, double-buffered partials in shared memory).
+//     xhat = (x - mean) rstd      g = dh (1 + scale_b) [w]        dshift_b += dh      dscale_b += dh xhat [w]    [dw += dh (1 + scale_b) xhat]
+//     dx  += rstd (g - mean(g) - xhat mean(g xhat))                (RMSNorm: no mean(g) term)
+//     HAS_GATE:   dy = mask (dx) gate_b rs_b (bf16)     dgate_b += rs_b sum dx y     dxsum_b += sum mask(dx)
+// Traffic per row element: dh 2 + x 4 + dx 4 + 4 (+ y 2 + dy 2) bytes = 14 (18) vs 14 + 6 (+ 8) for the separate kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int AGB_ROWS = 4;
+
+template <int NORM_KIND, int HAS_GATE, int MAXT>  // MAXT = 320: two CTAs per SM (<= 102 registers), else 512 threads, one CTA
+__global__ void __launch_bounds__(MAXT, MAXT <= 320 ? 2 : 1)
+adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float2* __restrict__ rowstats,
+                      const float* __restrict__ scale, long long mod_bstride, const float* __restrict__ weight,
+                      float* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_bstride,
+                      float* __restrict__ dweight, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+                      __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dxsum, DropCfg drop,
+                      const float* __restrict__ rowscale, int D, int tokens_per_batch, int rows_per_cta) {
+    constexpr int R = AGB_ROWS;
+    __shared__ float4 red[2][16][2];  // [buffer][warp][sum g | sum g xhat] for the R rows of a group
+    const int c4 = threadIdx.x, lane = c4 & 31, warp = c4 >> 5, nw = (int)(blockDim.x >> 5);
+    const bool act = c4 < (D >> 2);
+    const int b = blockIdx.y;
+    const float inv_d = 1.0f / (float)D;
+    float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), w4 = sc4, g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rs = 1.0f;
+    if (act) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * mod_bstride) + c4);
+        sc4 = make_float4(1.0f + t.x, 1.0f + t.y, 1.0f + t.z, 1.0f + t.w);
+        if (NORM_KIND == 1) w4 = __ldg(reinterpret_cast<const float4*>(weight) + c4);
+        if (HAS_GATE) {
+            rs = rowscale != nullptr ? __ldg(rowscale + b) : 1.0f;
+            g4 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride) + c4);
+            g4.x *= rs; g4.y *= rs; g4.z *= rs; g4.w *= rs;
+        }
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a_shift = zero4, a_scale = zero4, a_w = zero4, a_gate = zero4, a_sum = zero4;
+    const int n0 = blockIdx.x * rows_per_cta;
+    const int n1 = min(n0 + rows_per_cta, tokens_per_batch);
+    const long long row0 = (long long)b * tokens_per_batch;
+    int buf = 0;
+    for (int n = n0; n < n1; n += R) {
+        float4 xv[R], gv[R], ov[R];
+        uint2 yv[R];
+        float rstd[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = act && n + r < n1;
+            const long long row = row0 + n + r;
+            const float2 st = ok ? __ldg(rowstats + row) : make_float2(0.f, 0.f);
+            const float4 xr = ok ? __ldcs(reinterpret_cast<const float4*>(x + row * D) + c4) : zero4;
+            gv[r] = ok ? bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(dh + row * D) + c4)) : zero4;
+            ov[r] = ok ? __ldcs(reinterpret_cast<const float4*>(dx + row * D) + c4) : zero4;
+            if (HAS_GATE) yv[r] = ok ? __ldcs(reinterpret_cast<const uint2*>(y + row * D) + c4) : make_uint2(0u, 0u);
+            rstd[r] = st.y;
+            xv[r] = make_float4((xr.x - st.x) * st.y, (xr.y - st.x) * st.y, (xr.z - st.x) * st.y, (xr.w - st.x) * st.y);
+        }
+        float sg[R], sgx[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 d = gv[r], xh = xv[r];
+            a_shift.x += d.x; a_shift.y += d.y; a_shift.z += d.z; a_shift.w += d.w;
+            a_scale.x += d.x * xh.x * w4.x; a_scale.y += d.y * xh.y * w4.y; a_scale.z += d.z * xh.z * w4.z; a_scale.w += d.w * xh.w * w4.w;
+            float4 g = make_float4(d.x * sc4.x, d.y * sc4.y, d.z * sc4.z, d.w * sc4.w);
+            if (NORM_KIND == 1) {
+                a_w.x += g.x * xh.x; a_w.y += g.y * xh.y; a_w.z += g.z * xh.z; a_w.w += g.w * xh.w;
+                g.x *= w4.x; g.y *= w4.y; g.z *= w4.z; g.w *= w4.w;
+            }
+            gv[r] = g;
+            sg[r] = (g.x + g.y) + (g.z + g.w);
+            sgx[r] = (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (NORM_KIND == 0) sg[r] += __shfl_xor_sync(0xffffffffu, sg[r], o);
+                sgx[r] += __shfl_xor_sync(0xffffffffu, sgx[r], o);
+            }
+        }
+        if (lane == 0) {
+            red[buf][warp][0] = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            red[buf][warp][1] = make_float4(sgx[0], sgx[1], sgx[2], sgx[3]);
+        }
+        __syncthreads();
+        float4 tg = zero4, tgx = zero4;
+        for (int w = 0; w < nw; ++w) {
+            const float4 p0 = red[buf][w][0], p1 = red[buf][w][1];
+            tg.x += p0.x; tg.y += p0.y; tg.z += p0.z; tg.w += p0.w;
+            tgx.x += p1.x; tgx.y += p1.y; tgx.z += p1.z; tgx.w += p1.w;
+        }
+        buf ^= 1;
+        const float mgs[R] = {tg.x * inv_d, tg.y * inv_d, tg.z * inv_d, tg.w * inv_d};
+        const float mgxs[R] = {tgx.x * inv_d, tgx.y * inv_d, tgx.z * inv_d, tgx.w * inv_d};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!(act && n + r < n1)) continue;
+            const long long row = row0 + n + r;
+            const float mg = NORM_KIND == 0 ? mgs[r] : 0.0f, mgx = mgxs[r], rd = rstd[r];
+            float4 o;
+            o.x = rd * (gv[r].x - mg - xv[r].x * mgx) + ov[r].x;
+            o.y = rd * (gv[r].y - mg - xv[r].y * mgx) + ov[r].y;
+            o.z = rd * (gv[r].z - mg - xv[r].z * mgx) + ov[r].z;
+            o.w = rd * (gv[r].w - mg - xv[r].w * mgx) + ov[r].w;
+            reinterpret_cast<float4*>(dx + row * D)[c4] = o;
+            if (HAS_GATE) {
+                const float4 yf = bf16x4_to_f32(yv[r]);
+                a_gate.x += o.x * yf.x; a_gate.y += o.y * yf.y; a_gate.z += o.z * yf.z; a_gate.w += o.w * yf.w;
+                float4 dm = o;
+                if (drop.thresh != 0u) {
+                    const uint32_t rr = (uint32_t)row, cc = (uint32_t)(c4 * 4);
+                    float m0, m1, m2, m3;
+                    drop_scale2(drop, rr, cc, m0, m1);
+                    drop_scale2(drop, rr, cc + 2, m2, m3);
+                    dm.x *= m0; dm.y *= m1; dm.z *= m2; dm.w *= m3;
+                }
+                a_sum.x += dm.x; a_sum.y += dm.y; a_sum.z += dm.z; a_sum.w += dm.w;
+                reinterpret_cast<uint2*>(dy + row * D)[c4] =
+                    make_uint2(pack_bf16(dm.x * g4.x, dm.y * g4.y), pack_bf16(dm.z * g4.z, dm.w * g4.w));
+            }
+        }
+    }
+    if (!act) return;
+    float* p1 = dshift + (long long)b * dmod_bstride + c4 * 4;
+    float* p2 = dscale + (long long)b * dmod_bstride + c4 * 4;
+    atomicAdd(p1, a_shift.x); atomicAdd(p1 + 1, a_shift.y); atomicAdd(p1 + 2, a_shift.z); atomicAdd(p1 + 3, a_shift.w);
+    atomicAdd(p2, a_scale.x); atomicAdd(p2 + 1, a_scale.y); atomicAdd(p2 + 2, a_scale.z); atomicAdd(p2 + 3, a_scale.w);
+    if (NORM_KIND == 1 && dweight != nullptr) {
+        float* p3 = dweight + c4 * 4;
+        atomicAdd(p3, a_w.x); atomicAdd(p3 + 1, a_w.y); atomicAdd(p3 + 2, a_w.z); atomicAdd(p3 + 3, a_w.w);
+    }
+    if (HAS_GATE) {
+        float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
+        atomicAdd(dg, a_gate.x * rs); atomicAdd(dg + 1, a_gate.y * rs); atomicAdd(dg + 2, a_gate.z * rs); atomicAdd(dg + 3, a_gate.w * rs);
+        if (dxsum != nullptr) {
+            float* ds = dxsum + (long long)b * D + c4 * 4;
+            atomicAdd(ds, a_sum.x); atomicAdd(ds + 1, a_sum.y); atomicAdd(ds + 2, a_sum.z); atomicAdd(ds + 3, a_sum.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix: out[c] += sum_m a[m, c]   (bias gradients of mlp.0, patch_embed, final_layer, ...).
 // grid = (ceil(cols / 512), row chunks); thread = 4 adjacent columns (8-byte loads), rows strided by the chunk count,
 // 8 loads in flight per thread.

@@ -19,7 +19,9 @@ template <int NV, int NORM_KIND>
 __global__ void __launch_bounds__(ADALN_WARPS * 32)
 adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                            const float* __restrict__ shift, const float* __restrict__ scale, long long mod_bstride,
-                           const float* __restrict__ weight, float eps, int M, int D, int tokens_per_batch) {
+                           const float* __restrict__ weight, float eps, int M, int D, int tokens_per_batch,
+                           float2* __restrict__ rowstats, float* __restrict__ x_copy) {
+    // rowstats / x_copy (training forward, optional): the row's (mean, rstd) and an f32 copy of the row, kept for the backward
     pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const int row = blockIdx.x * ADALN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -32,6 +34,12 @@ adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restric
     for (int i = 0; i < NV; ++i) {
         const int idx = lane + 32 * i;
         v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (x_copy != nullptr) {
+        float4* cr = reinterpret_cast<float4*>(x_copy + (long long)row * D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (lane + 32 * i < nvec) __stcs(cr + lane + 32 * i, v[i]);
     }
     const float inv_d = 1.0f / (float)D;
     float mean = 0.f, rstd;
@@ -56,6 +64,7 @@ adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restric
         rstd = rsqrtf(warp_sum(q) * inv_d + eps);
     }
 
+    if (rowstats != nullptr && lane == 0) rowstats[row] = make_float2(mean, rstd);
     const bool has_mod = shift != nullptr;
     const long long boff = has_mod ? (long long)(row / tokens_per_batch) * mod_bstride : 0;
     const float4* sh = has_mod ? reinterpret_cast<const float4*>(shift + boff) : nullptr;

@@ -215,7 +215,7 @@ class TrainBuffers:
         self.saved = dict(x_in=f32(depth, M, D), x_mid=f32(depth, M, D), h1=bf(depth, M, D), qkv=bf(depth, M, qkv),
                           attn=bf(depth, M, D), lse=f32(depth, B, Hq, N), y1=bf(depth, M, D), h2=bf(depth, M, D),
                           u=bf(depth, M, F), mact=bf(depth, M, F), y2=bf(depth, M, D), pe_u=bf(M, BD), t_u1=bf(B, D),
-                          t_u2=bf(B, D))
+                          t_u2=bf(B, D), rs1=f32(depth, M, 2), rs2=f32(depth, M, 2))
         NM = depth * 6 * D
         self.scratch = dict(dx=f32(M, D), dy=bf(M, D), dh=bf(M, D), da=bf(M, D), du=bf(M, F), dqkv=bf(M, qkv),
                             dsum=f32(B, Hq, N), dq_acc=f32(M, Hq * attn0.head_dim), dmod=f32(depth, B, 6 * D),

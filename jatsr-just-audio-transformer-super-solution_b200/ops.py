@@ -224,6 +224,27 @@ def gate_bwd(dx, y, gate, B, tokens_per_batch, dgate, *, mod_batch_stride=0, dmo
     return dy
 
 
+def adaln_gate_bwd(dh, x, rowstats, B, tokens_per_batch, dx, *, scale, mod_batch_stride, dshift, dscale, dmod_batch_stride,
+                   weight=None, norm_kind=L.NORM_LAYERNORM, dweight=None, y=None, gate=None, dgate=None, dy=None, dbias=None,
+                   drop_p=0.0, drop_seed=0, gate_rowscale=None):
+    """Fused norm + modulate backward (dx accumulated in place, dshift / dscale [/ dweight] atomically added) and, when `y`
+    is given, the gate backward of the branch below on the updated dx row (-> dy bf16, dgate [, dbias])."""
+    _chk(dh, torch.bfloat16, "dh")
+    _chk(x, torch.float32, "x")
+    _chk(dx, torch.float32, "dx")
+    _chk(rowstats, torch.float32, "rowstats")
+    D = x.shape[1]
+    if y is not None and dy is None:
+        dy = torch.empty_like(y)
+    scratch = torch.empty(B, D, dtype=torch.float32, device=dx.device) if dbias is not None else None
+    L.check(L.load().jat_adaln_gate_bwd(_ctx(x), dh.data_ptr(), x.data_ptr(), rowstats.data_ptr(), scale.data_ptr(),
+                                        mod_batch_stride, _p(weight), norm_kind, dx.data_ptr(), dshift.data_ptr(),
+                                        dscale.data_ptr(), dmod_batch_stride, _p(dweight), _p(y), _p(gate), _p(dy), _p(dgate),
+                                        _p(scratch), _p(dbias), B, tokens_per_batch, D, float(drop_p), int(drop_seed),
+                                        _p(gate_rowscale), _stream(x.device)))
+    return dy
+
+
 def colsum_bf16(a, out):
     _chk(a, torch.bfloat16, "a")
     L.check(L.load().jat_colsum_bf16(_ctx(a), a.data_ptr(), a.stride(0), a.shape[0], a.shape[1], out.data_ptr(),

@@ -588,6 +588,60 @@ def test_gate_bwd_matches_autograd(ops, with_bias):
         assert rel_l2(dbias - 1, (g * dx).sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("norm_kind", [0, 1])
+@pytest.mark.parametrize("D,B,Ntok", [(1280, 28, 345), (1280, 3, 77), (128, 4, 22), (1000, 2, 5)])
+@pytest.mark.parametrize("gate_mode", ["none", "gate", "gate_bias_drop"])
+def test_adaln_gate_bwd_fused_matches_autograd(ops, L, norm_kind, D, B, Ntok, gate_mode):
+    """Fused norm + modulate backward (+ the gate backward of the branch below, on the updated dx row) against torch
+    autograd of   h = norm(x) (1 + scale_b) + shift_b   and   x_out = x_in + rs_b gate_b mask (y)."""
+    torch.manual_seed(41)
+    M = B * Ntok
+    x = (torch.randn(M, D, device=dev()) * 1.3 + 0.2).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(D, device=dev())).requires_grad_(True)
+    mod = (0.3 * torch.randn(B, 3 * D, device=dev())).requires_grad_(True)     # shift | scale | gate, row stride 3D
+    shift, scale, gate = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:]
+    dh = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+    if norm_kind == 0:
+        yn = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+        mean, rstd = x.mean(-1), torch.rsqrt(x.var(-1, unbiased=False) + 1e-6)
+    else:
+        rstd = torch.rsqrt((x * x).mean(-1) + 1e-6)
+        mean = torch.zeros_like(rstd)
+        yn = x * rstd[:, None] * w
+    h = yn * (1 + scale.repeat_interleave(Ntok, 0)) + shift.repeat_interleave(Ntok, 0)
+    rowstats = torch.stack([mean, rstd], -1).detach().contiguous()
+    base = torch.randn(M, D, device=dev())                                     # gradient already on the residual stream
+    (gx,) = torch.autograd.grad(h, x, dh.float(), retain_graph=True)
+    dx_want = base + gx
+    dmod = torch.zeros(B, 3 * D, device=dev())
+    dw = torch.zeros(D, device=dev())
+    kw = dict(scale=scale.detach(), mod_batch_stride=3 * D, dshift=dmod[:, :D], dscale=dmod[:, D:2 * D], dmod_batch_stride=3 * D,
+              norm_kind=norm_kind, weight=w.detach() if norm_kind else None, dweight=dw if norm_kind else None)
+    dx = base.clone()
+    if gate_mode == "none":
+        ops.adaln_gate_bwd(dh, x.detach(), rowstats, B, Ntok, dx, **kw)
+    else:
+        drop = gate_mode == "gate_bias_drop"
+        p, seed = (0.1, 77) if drop else (0.0, 0)
+        yb = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+        rs = (torch.rand(B, device=dev()) > 0.3).float() / 0.7 if drop else None
+        dbias = torch.ones(D, device=dev()) if drop else None
+        dy = ops.adaln_gate_bwd(dh, x.detach(), rowstats, B, Ntok, dx, y=yb, gate=gate.detach(), dgate=dmod[:, 2 * D:], dbias=dbias,
+                                drop_p=p, drop_seed=seed, gate_rowscale=rs, **kw)
+        mask = ops.dropout_scale_mask(M, D, p, seed, dev()) if drop else torch.ones(M, D, device=dev())
+        g_eff = (gate.detach() * (rs[:, None] if rs is not None else 1.0)).repeat_interleave(Ntok, 0)
+        assert rel_l2(dy.float(), dx_want * mask * g_eff) < 4e-3               # bf16 output
+        want_dgate = (dx_want * yb.float()).view(B, Ntok, D).sum(1) * (rs[:, None] if rs is not None else 1.0)
+        assert rel_l2(dmod[:, 2 * D:], want_dgate) < 2e-5
+        if drop:
+            assert rel_l2(dbias - 1, (dx_want * mask * g_eff).sum(0)) < 2e-5
+    assert rel_l2(dx, dx_want) < 2e-5
+    h.backward(dh.float())
+    assert rel_l2(dmod[:, :D], mod.grad[:, :D]) < 1e-5 and rel_l2(dmod[:, D:2 * D], mod.grad[:, D:2 * D]) < 1e-5
+    if norm_kind:
+        assert rel_l2(dw, w.grad) < 1e-5
+
+
 def test_colsum_and_cast(ops):
     torch.manual_seed(23)
     a = torch.randn(9660, 512, device=dev()).to(torch.bfloat16)
