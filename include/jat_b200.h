@@ -397,7 +397,7 @@ int jat_profile_end(jat_ctx* ctx, int max_tags, const char** names, double* tota
  * backward, for callers that kept the row statistics of the forward norm: rowstats f32 [M, 2] = (mean, rstd) per token row
  * (what jat_dit_forward_train writes to jat_dit_saved.rs1 / rs2).  One pass over dh, x and dx: dx += norm backward,
  * dshift / dscale (/ dweight) += column sums; and, when y_bf16 != NULL, on the updated dx row: dy = dropout-mask(dx) *
- * gate_b * rowscale_b (bf16), dgate_b += rowscale_b * sum_n dx * y, dbias (optional, needs dxsum_scratch f32 [B, D]).
+ * gate_b * rowscale_b (bf16), dgate_b += rowscale_b * sum_n dx * y, dbias[:] += rowscale_b gate_b sum_n mask(dx) (optional; dxsum_scratch is unused, may be NULL).
  * scale and gate share mod_batch_stride; dshift / dscale / dgate share dmod_batch_stride. */
 int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* rowstats, const float* scale,
                        int64_t mod_batch_stride, const float* weight, int norm_kind, float* dx, float* dshift, float* dscale,
@@ -418,7 +418,7 @@ int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const 
  *   dweight[D] += RMSNorm weight gradient (RMSNorm only, may be NULL).  rowstats_scratch: f32 [M, 2] (row mean / rstd
  *   handed from the row-wise dx kernel to the column-sum kernel; may be NULL when scale == dweight == NULL).
  * jat_gate_bwd: backward of x += gate_b * y:  dy bf16 = gate_b * dx;  dgate[b,:] += sum_n dx * y;
- *   if dbias != NULL: dbias[:] += sum_b gate_b * sum_n dx (uses dxsum_scratch f32 [B, D]).
+ *   if dbias != NULL: dbias[:] += sum_b gate_b * sum_n dx (f32 atomics; dxsum_scratch is unused and may be NULL).
  * jat_colsum_bf16: out[c] += sum_m a[m, c] (bias gradients).    jat_cast_f32_bf16: elementwise cast.
  * -------------------------------------------------------------------------------------------- */
 int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* scale, int64_t mod_batch_stride,

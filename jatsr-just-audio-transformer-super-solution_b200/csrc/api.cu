@@ -718,23 +718,15 @@ extern "C" int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y
     DropCfg drop;
     if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: drop_p must be in [0, 1)");
     if (!ctx || !dx || !y_bf16 || !gate || !dy_bf16 || !dgate) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: null argument");
-    if (dbias != nullptr && dxsum_scratch == nullptr) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: dbias needs the [B, D] scratch");
     if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gate_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
     cudaStream_t s = (cudaStream_t)stream;
-    float* xs = dbias ? dxsum_scratch : nullptr;
-    if (xs) JAT_CUDA(cudaMemsetAsync(xs, 0, (size_t)B * D * sizeof(float), s));
+    (void)dxsum_scratch;  // no longer used: the bias gradient is accumulated by the kernel itself
     dim3 grid((tokens_per_batch + BWD_ROWS_PER_CTA - 1) / BWD_ROWS_PER_CTA, B), block((D / 4 + 31) / 32 * 32);
     pre_launch(ctx, TAG_GATE_BWD, s);
     gate_bwd_kernel<<<grid, block, 0, s>>>(dx, (const __nv_bfloat16*)y_bf16, gate, mod_batch_stride, (__nv_bfloat16*)dy_bf16,
-                                           dgate, dmod_batch_stride, xs, D, tokens_per_batch, drop, gate_rowscale);
-    JAT_TRY(post_launch(ctx, "gate_bwd"));
-    if (dbias) {
-        pre_launch(ctx, TAG_GATE_BWD, s);
-        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D, gate_rowscale);
-        return post_launch(ctx, "gate_bias_grad");
-    }
-    return 0;
+                                           dgate, dmod_batch_stride, dbias, D, tokens_per_batch, drop, gate_rowscale);
+    return post_launch(ctx, "gate_bwd");
 }
 
 extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, const float* rowstats, const float* scale,
@@ -747,8 +739,8 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
         return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: null argument");
     const bool has_gate = y_bf16 != nullptr;
     if (has_gate && (!gate || !dy_bf16 || !dgate)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: gate / dy / dgate missing");
-    if (dbias != nullptr && (!has_gate || dxsum_scratch == nullptr))
-        return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: dbias needs the gate part and the [B, D] scratch");
+    if (dbias != nullptr && !has_gate) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: dbias needs the gate part");
+    (void)dxsum_scratch;
     if (B <= 0 || B > 65535 || tokens_per_batch <= 0 || D <= 0 || D % 4 != 0 || D > 2048)
         return fail(JAT_ERR_BAD_SHAPE, "jat_adaln_gate_bwd: need D %% 4 == 0, D <= 2048, 0 < B <= 65535");
     if (mod_batch_stride % 4 != 0 || dmod_batch_stride % 4 != 0)
@@ -759,8 +751,7 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
     DropCfg drop;
     if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: drop_p must be in [0, 1)");
     cudaStream_t s = (cudaStream_t)stream;
-    float* xs = dbias ? dxsum_scratch : nullptr;
-    if (xs) JAT_CUDA(cudaMemsetAsync(xs, 0, (size_t)B * D * sizeof(float), s));
+    float* xs = dbias;
     // one wave: two CTAs of D/4 threads per SM, every batch item cut into the same number of row ranges
     int per_batch = (2 * ctx->sm_count) / B;
     if (per_batch < 1) per_batch = 1;
@@ -783,13 +774,7 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
     if (norm_kind == JAT_NORM_LAYERNORM) { if (has_gate) JAT_AGB(0, 1); else JAT_AGB(0, 0); }
     else { if (has_gate) JAT_AGB(1, 1); else JAT_AGB(1, 0); }
 #undef JAT_AGB
-    JAT_TRY(post_launch(ctx, "adaln_gate_bwd"));
-    if (dbias) {
-        pre_launch(ctx, TAG_GATE_BWD, s);
-        gate_bias_grad_kernel<<<(D + 255) / 256, 256, 0, s>>>(gate, mod_batch_stride, xs, dbias, B, D, gate_rowscale);
-        return post_launch(ctx, "gate_bias_grad");
-    }
-    return 0;
+    return post_launch(ctx, "adaln_gate_bwd");
 }
 
 extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream) {
@@ -1050,7 +1035,7 @@ extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, cons
     const uint64_t rows = (uint64_t)B * N, qcols = (uint64_t)Hq * ATT_HD, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     JAT_CUDA(cudaMemsetAsync(dq_acc_scratch, 0, rows * qcols * sizeof(float), s));
     {
-        const long long n = (long long)rows * Hq;
+        const long long n = (long long)rows * Hq * 8;
         pre_launch(ctx, TAG_ATTN_BWD, s);
         attn_bwd_rowdot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)d_out, (const __nv_bfloat16*)out,
                                                                          dsum_scratch, B, N, Hq);
@@ -1346,7 +1331,10 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
     const void* mact = at(sv->mact, i, (int64_t)M * F, 2);
     const float pd = sv->dropout_p;
     const float* dps = sv->drop_path_rates != nullptr ? sv->dp_scale : nullptr;
+    const bool fused = sv->rs1 != nullptr && sv->rs2 != nullptr;
     // ---- MLP branch: x2 = x1 + drop_path(gate_mlp * drop(drop(gelu(h2 W1^T + b1)) W2^T + b2))
+    // (fused path: the norm1 backward of block i + 1 has already done this gate backward on the dx rows it produced)
+    if (!fused || i == w->depth - 1)
     JAT_TRY(jat_gate_bwd_dropout(ctx, sc->dx, at(sv->y2, i, MD, 2), m + 5 * D, NM, sc->dy, dm + 5 * D, d.SIXD, sc->dxsum,
                                  (float*)gr->b2[i], B, N, D, pd, jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_MLP_OUT),
                                  dps ? dps + (int64_t)(2 * i + 1) * B : nullptr, stream));
@@ -1356,7 +1344,6 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
     JAT_TRY(wgrad(ctx, sc->du, F, h2, D, (float*)gr->w1[i], F, D, M, stream));
     JAT_TRY(jat_colsum_bf16(ctx, sc->du, F, M, F, (float*)gr->b1[i], stream));
     JAT_TRY(dgrad(ctx, sc->du, F, w->w1[i], D, F, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
-    const bool fused = sv->rs1 != nullptr && sv->rs2 != nullptr;
     if (fused) {
         // norm2 backward + the gate backward of the attention branch below it (x1 = x + drop_path(gate_msa * (attn(h1) Wo^T)))
         JAT_TRY(jat_adaln_gate_bwd(ctx, sc->dh, (const float*)at(sv->x_mid, i, MD, 4), sv->rs2 + (int64_t)i * M * 2, m + 4 * D, NM,
@@ -1378,12 +1365,22 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
                                           jat_dropout_site_seed(sv->seed, i, JAT_DROP_SITE_ATTN), stream));
     JAT_TRY(wgrad(ctx, sc->dqkv, d.QKV, h1, D, (float*)gr->wqkv[i], d.QKV, D, M, stream));
     JAT_TRY(dgrad(ctx, sc->dqkv, d.QKV, w->wqkv[i], D, d.QKV, M, sc->dh, JAT_ACT_NONE, nullptr, stream));
-    if (fused)
+    if (fused && i > 0) {
+        // norm1 backward + the gate backward of the MLP branch of block i - 1 (the next stage), whose modulation row and
+        // gradient slab sit 6D before this block's: gate_mlp(i-1) = m - D, dgate_mlp(i-1) = dm - B*6D + 5D.  The kernel
+        // addresses gate / dgate with the strides of scale / dshift, so both are passed relative to this block's views.
+        JAT_TRY(jat_adaln_gate_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), sv->rs1 + (int64_t)i * M * 2, m + D, NM,
+                                   w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind, sc->dx, dm, dm + D, d.SIXD,
+                                   rms ? (float*)gr->norm1_w[i] : nullptr, at(sv->y2, i - 1, MD, 2), m - D, sc->dy,
+                                   dm - (int64_t)B * d.SIXD + 5 * D, nullptr, (float*)gr->b2[i - 1], B, N, D, pd,
+                                   jat_dropout_site_seed(sv->seed, i - 1, JAT_DROP_SITE_MLP_OUT),
+                                   dps ? dps + (int64_t)(2 * (i - 1) + 1) * B : nullptr, stream));
+    } else if (fused) {
         JAT_TRY(jat_adaln_gate_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), sv->rs1 + (int64_t)i * M * 2, m + D, NM,
                                    w->norm1_w ? w->norm1_w[i] : nullptr, w->norm_kind, sc->dx, dm, dm + D, d.SIXD,
                                    rms ? (float*)gr->norm1_w[i] : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B,
                                    N, D, 0.0f, 0u, nullptr, stream));
-    else
+    } else
     JAT_TRY(jat_adaln_bwd(ctx, sc->dh, (const float*)at(sv->x_in, i, MD, 4), m + D, NM, w->norm1_w ? w->norm1_w[i] : nullptr,
                           w->norm_kind, w->norm_eps, sc->dx, 1, dm, dm + D, d.SIXD, rms ? (float*)gr->norm1_w[i] : nullptr,
                           sc->rowstats, B, N, D, stream));

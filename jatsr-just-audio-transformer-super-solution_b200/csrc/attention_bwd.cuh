@@ -342,27 +342,35 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     }
 }
 
-// D[b, h, n] = sum_d dO[m, h*64 + d] * O[m, h*64 + d]   (one thread per (token row, head))
+// D[b, h, n] = sum_d dO[m, h*64 + d] * O[m, h*64 + d]   (8 lanes per (token row, head): one 16-byte load each, so a warp
+// reads 4 x 128 contiguous bytes of both operands; 3 shuffles finish the dot product)
 __global__ void attn_bwd_rowdot_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                        float* __restrict__ dsum, int B, int N, int Hq) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)B * N * Hq) return;
-    const int h = (int)(i % Hq);
-    const long long m = i / Hq;
-    const uint4* a = reinterpret_cast<const uint4*>(dO + m * (Hq * 64) + h * 64);
-    const uint4* c = reinterpret_cast<const uint4*>(O + m * (Hq * 64) + h * 64);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = t >> 3;  // (row, head); each group of 8 lanes is in or out of range together
+    const int k = (int)(t & 7);
+    const bool ok = i < (long long)B * N * Hq;
     float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint4 x = __ldg(a + k), y = __ldg(c + k);
+    int h = 0;
+    long long m = 0;
+    if (ok) {
+        h = (int)(i % Hq);
+        m = i / Hq;
+        const uint4 x = __ldcs(reinterpret_cast<const uint4*>(dO + m * (Hq * 64) + h * 64) + k);
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(O + m * (Hq * 64) + h * 64) + k);
         const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             s += __uint_as_float(xs[q] << 16) * __uint_as_float(ys[q] << 16) +
                  __uint_as_float(xs[q] & 0xffff0000u) * __uint_as_float(ys[q] & 0xffff0000u);
     }
-    const int bidx = (int)(m / N), n = (int)(m % N);
-    dsum[((long long)bidx * Hq + h) * N + n] = s;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok && k == 0) {
+        const int bidx = (int)(m / N), n = (int)(m % N);
+        dsum[((long long)bidx * Hq + h) * N + n] = s;
+    }
 }
 
 // dq (bf16, into the Q column range of dqkv) = inverse-RoPE(dQ accumulator f32 [M, Hq*64]); one thread per

@@ -172,14 +172,14 @@ adaln_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dh, const float* __res
 // ------------------------------------------------------------------------------------------------
 // Gate backward.  Forward (jat_audiosr_v2.py:281,287): x += gate_b * y.   Given the residual-stream gradient dx (f32)
 // and the saved y (bf16):   dy = gate_b * dx (bf16, the A operand of the following dgrad / wgrad GEMMs)
-//     dgate_b += sum_n dx * y          dxsum_b += sum_n dx   (db = sum_b gate_b * dxsum_b, finished by gate_bias_grad_kernel)
+//     dgate_b += sum_n dx * y          db += gate_b * sum_n dx   (bias of mlp.3; f32 atomics)
 // Thread = 4 fixed columns; a CTA (D/4 threads) walks over 32 token rows of one batch item, so every row access is one
 // fully coalesced 5 KB read and the column partials live in 8 registers -- no cross-thread reduction at all.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
                 long long mod_bstride, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dmod_bstride,
-                float* __restrict__ dxsum, int D, int tokens_per_batch, DropCfg drop, const float* __restrict__ rowscale) {
+                float* __restrict__ dbias, int D, int tokens_per_batch, DropCfg drop, const float* __restrict__ rowscale) {
     const int c4 = threadIdx.x;  // vec4 column
     if (c4 >= (D >> 2)) return;
     const int b = blockIdx.y;
@@ -211,21 +211,10 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
     }
     float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
     atomicAdd(dg, a_gate.x * rs); atomicAdd(dg + 1, a_gate.y * rs); atomicAdd(dg + 2, a_gate.z * rs); atomicAdd(dg + 3, a_gate.w * rs);
-    if (dxsum != nullptr) {
-        float* ds = dxsum + (long long)b * D + c4 * 4;
-        atomicAdd(ds, a_sum.x); atomicAdd(ds + 1, a_sum.y); atomicAdd(ds + 2, a_sum.z); atomicAdd(ds + 3, a_sum.w);
+    if (dbias != nullptr) {  // db += rs_b gate_b sum_n mask(dx)   (bias of mlp.3: y = acc + bias enters x through the gate)
+        float* ds = dbias + c4 * 4;
+        atomicAdd(ds, a_sum.x * g4.x); atomicAdd(ds + 1, a_sum.y * g4.y); atomicAdd(ds + 2, a_sum.z * g4.z); atomicAdd(ds + 3, a_sum.w * g4.w);
     }
-}
-
-// db[d] += sum_b gate[b, d] * dxsum[b, d]      (bias of mlp.3: y = acc + bias enters x through the gate)
-__global__ void gate_bias_grad_kernel(const float* __restrict__ gate, long long mod_bstride, const float* __restrict__ dxsum,
-                                      float* __restrict__ dbias, int B, int D, const float* __restrict__ rowscale) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b)
-        s += gate[(long long)b * mod_bstride + d] * (rowscale != nullptr ? rowscale[b] : 1.0f) * dxsum[(long long)b * D + d];
-    dbias[d] += s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,7 +226,7 @@ __global__ void gate_bias_grad_kernel(const float* __restrict__ gate, long long 
 // (warp shuffles + one __syncthreads per group, double-buffered partials in shared memory).
 //     xhat = (x - mean) rstd      g = dh (1 + scale_b) [w]        dshift_b += dh      dscale_b += dh xhat [w]    [dw += dh (1 + scale_b) xhat]
 //     dx  += rstd (g - mean(g) - xhat mean(g xhat))                (RMSNorm: no mean(g) term)
-//     HAS_GATE:   dy = mask (dx) gate_b rs_b (bf16)     dgate_b += rs_b sum dx y     dxsum_b += sum mask(dx)
+//     HAS_GATE:   dy = mask (dx) gate_b rs_b (bf16)     dgate_b += rs_b sum dx y     db += rs_b gate_b sum mask(dx)
 // Traffic per row element: dh 2 + x 4 + dx 4 + 4 (+ y 2 + dy 2) bytes = 14 (18) vs 14 + 6 (+ 8) for the separate kernels.
 // ------------------------------------------------------------------------------------------------
 constexpr int AGB_ROWS = 4;
@@ -248,7 +237,7 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
                       const float* __restrict__ scale, long long mod_bstride, const float* __restrict__ weight,
                       float* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_bstride,
                       float* __restrict__ dweight, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
-                      __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dxsum, DropCfg drop,
+                      __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dbias, DropCfg drop,
                       const float* __restrict__ rowscale, int D, int tokens_per_batch, int rows_per_cta) {
     constexpr int R = AGB_ROWS;
     __shared__ float4 red[2][16][2];  // [buffer][warp][sum g | sum g xhat] for the R rows of a group
@@ -367,9 +356,9 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
     if (HAS_GATE) {
         float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
         atomicAdd(dg, a_gate.x * rs); atomicAdd(dg + 1, a_gate.y * rs); atomicAdd(dg + 2, a_gate.z * rs); atomicAdd(dg + 3, a_gate.w * rs);
-        if (dxsum != nullptr) {
-            float* ds = dxsum + (long long)b * D + c4 * 4;
-            atomicAdd(ds, a_sum.x); atomicAdd(ds + 1, a_sum.y); atomicAdd(ds + 2, a_sum.z); atomicAdd(ds + 3, a_sum.w);
+        if (dbias != nullptr) {
+            float* ds = dbias + c4 * 4;
+            atomicAdd(ds, a_sum.x * g4.x); atomicAdd(ds + 1, a_sum.y * g4.y); atomicAdd(ds + 2, a_sum.z * g4.z); atomicAdd(ds + 3, a_sum.w * g4.w);
         }
     }
 }
