@@ -376,6 +376,10 @@ int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_
 /* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
 int64_t jat_launch_count(const jat_ctx* ctx);
 
+/* Leave `reserve` SMs out of the persistent GEMM grids (default 0; env JAT_SM_RESERVE).  For DDP training: the GEMMs are
+ * persistent one-CTA-per-SM kernels with a static tile schedule, so an NCCL all-reduce kernel that holds a few SMs would
+ * make every GEMM launched meanwhile wait for it; with a reserve the two run side by side. */
+int jat_set_gemm_sm_reserve(jat_ctx* ctx, int reserve);
 /* Default GEMM tile configuration used when a call passes cta_pair < 0 / block_n == 0. */
 int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n);
 /* Tail split (default off): when the persistent tile schedule ends in a partial wave, the tiles of that wave are cut

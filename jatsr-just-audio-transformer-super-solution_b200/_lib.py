@@ -129,6 +129,7 @@ SIGNATURES = {
     "jat_launch_count": (_i64, [_vp]),
     "jat_set_gemm_config": (_i, [_vp, _i, _i]),
     "jat_set_gemm_tail_split": (_i, [_vp, _i]),
+    "jat_set_gemm_sm_reserve": (_i, [_vp, _i]),
     "jat_debug_set_attention_trace": (_i, [_vp, _vp]),
     "jat_debug_set_gemm_trace": (_i, [_vp, _vp]),
     "jat_profile_begin": (_i, [_vp]),

@@ -32,6 +32,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct jat_ctx {
     int device;
     int sm_count;
+    int gemm_sms;          // SMs the persistent GEMM grids occupy (sm_count minus the reserve for concurrent NCCL kernels)
     PFN_encodeTiled encode;
     std::atomic<long long> launches;
     int gemm_cta_pair;  // default tile configuration (overridable per call)
@@ -105,6 +106,11 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     if (!c) return fail(JAT_ERR_BAD_ARG, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->gemm_sms = c->sm_count;
+    if (getenv("JAT_SM_RESERVE")) {
+        const int r = atoi(getenv("JAT_SM_RESERVE"));
+        if (r > 0 && r < c->sm_count - 8) c->gemm_sms = (c->sm_count - r) & ~1;
+    }
     c->encode = (PFN_encodeTiled)fn;
     c->launches.store(0);
     c->gemm_cta_pair = 1;  // CTA pairs (cta_group::2) by default: half the B-operand smem traffic per SM
@@ -139,6 +145,13 @@ extern "C" void jat_destroy(jat_ctx* ctx) {
     delete ctx;
 }
 extern "C" int jat_sm_count(const jat_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int jat_set_gemm_sm_reserve(jat_ctx* ctx, int reserve) {
+    if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
+    if (reserve < 0 || reserve > ctx->sm_count - 8) return fail(JAT_ERR_BAD_ARG, "jat_set_gemm_sm_reserve: reserve out of range");
+    ctx->gemm_sms = (ctx->sm_count - reserve) & ~1;
+    return 0;
+}
 extern "C" int64_t jat_launch_count(const jat_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 extern "C" int jat_set_gemm_config(jat_ctx* ctx, int cta_pair, int block_n) {
     if (!ctx) return fail(JAT_ERR_BAD_ARG, "ctx == NULL");
@@ -311,7 +324,7 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
         JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    int clusters = ctx->sm_count / (CG * MC);
+    int clusters = ctx->gemm_sms / (CG * MC);
     const int num_work = p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
     if (clusters > num_work) clusters = num_work;
     cudaLaunchConfig_t cfg = {};
@@ -482,7 +495,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     p.tail_ws = ctx->tail_ws;
     p.tail_cnt = ctx->tail_cnt;
     {
-        const int clusters = ctx->sm_count / cg;
+        const int clusters = ctx->gemm_sms / cg;
         const int rem = p.num_tiles % clusters;
         // mode 2: reduce-add epilogues without a pre-gate copy only -- every part runs the ordinary epilogue on its
         // partial sum (bias with part 0), so there is no workspace round trip; the f32 adds of the parts of one tile land
@@ -1260,7 +1273,7 @@ static int wgrad(jat_ctx* ctx, const void* dY, int64_t ld_dy, const void* X, int
     const int kblocks = (Mtok + GEMM_BK - 1) / GEMM_BK;
     // split the token reduction s ways so that the persistent schedule's makespan is shortest: every CTA pair runs
     // ceil(tiles * s / pairs) items of ceil(kblocks / s) k-blocks each, plus ~4 k-blocks' worth of f32 reduce-add epilogue
-    const long long pairs = ctx->sm_count / 2;
+    const long long pairs = ctx->gemm_sms / 2;
     long long best = 1, best_cost = -1;
     for (long long sp = 1; sp <= 8 && sp <= kblocks; ++sp) {
         const long long cost = ((tiles * sp + pairs - 1) / pairs) * ((kblocks + sp - 1) / sp + 4);

@@ -113,6 +113,13 @@ def set_gemm_tail_split(device, mode):
     L.check(L.load().jat_set_gemm_tail_split(L.context(idx), int(mode)))
 
 
+def set_gemm_sm_reserve(device, reserve):
+    """Keep `reserve` SMs out of the persistent GEMM grids of a device's context (room for concurrent NCCL kernels)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    L.check(L.load().jat_set_gemm_sm_reserve(L.context(idx), int(reserve)))
+
+
 def gqa_attention_fwd(qkv, B, N, Hq, Hkv, head_dim=64, out=None, lse=None, drop_p=0.0, drop_seed=0):
     """lse: optional f32 [B, Hq, N] output (log2-domain log-sum-exp per query row, for the backward pass).
     drop_p / drop_seed: train-mode dropout on the probabilities (mask row = (b*Hq + h)*N + query, col = key)."""
