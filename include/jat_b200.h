@@ -361,17 +361,19 @@ typedef struct jat_adamw_tensor {
     int64_t numel;
     int32_t packed_dtype;
     int32_t vec_ok;
+    float bias_corr1;      /* 1 - beta1^step of this tensor (step counts from 1, after the increment of this update) */
+    float bias_corr2_sqrt; /* sqrt(1 - beta2^step) */
 } jat_adamw_tensor;
 int jat_adamw_chunk_elems(void);
 /* sumsq_dev[0] (+)= sum over all table entries of grad^2 (f32 per-chunk partials in partials_dev [total_chunks], summed in
  * chunk order in f64: bit-reproducible).  accumulate != 0 adds to the existing value (several parameter groups). */
 int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
                    int total_chunks, float* partials_dev, double* sumsq_dev, int accumulate, void* stream);
-/* AdamW (decoupled weight decay, no amsgrad) on every table entry; step counts from 1.  max_norm > 0: the gradients are
+/* AdamW (decoupled weight decay, no amsgrad) on every table entry, bias corrections per entry.  max_norm > 0: the gradients are
  * scaled by min(1, max_norm / (sqrt(*sumsq_dev) + 1e-6)) on the fly (clip_grad_norm_; `grad` itself is not modified). */
 int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
-                   int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                   float max_norm, const double* sumsq_dev, void* stream);
+                   int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay, float max_norm,
+                   const double* sumsq_dev, void* stream);
 
 /* Number of kernels the library has launched on this context since creation (bench `gpu_launches`). */
 int64_t jat_launch_count(const jat_ctx* ctx);

@@ -119,8 +119,7 @@ SIGNATURES = {
     "jat_gate_bwd_dropout": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _f, _u32, _vp, _vp]),
     "jat_adamw_chunk_elems": (_i, []),
     "jat_grad_sumsq": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
-    "jat_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _f, _vp,
-                            _vp]),
+    "jat_adamw_step": (_i, [_vp, _vp, _vp, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _f, _vp, _vp]),
     "jat_abi_version": (_i, []),
     "jat_last_error": (C.c_char_p, []),
     "jat_create": (_i, [_i, C.POINTER(_vp)]),

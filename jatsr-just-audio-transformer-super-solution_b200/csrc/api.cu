@@ -873,23 +873,19 @@ extern "C" int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, c
 
 extern "C" int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
                               int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay,
-                              int64_t step, float max_norm, const double* sumsq_dev, void* stream) {
+                              float max_norm, const double* sumsq_dev, void* stream) {
     JAT_TRY(opt_check("jat_adamw_step", ctx, table_dev, chunk_first_dev, n_tensors, total_chunks));
-    if (step < 1) return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: step counts from 1 (got %lld)", (long long)step);
     if (!(lr >= 0.0) || !(eps >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(weight_decay >= 0.0))
         return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: hyper-parameter out of range");
     if (max_norm > 0.f && !sumsq_dev) return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: clipping needs the gradient sum of squares");
     AdamWArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
-    a.bias_corr1 = (float)(1.0 - pow(beta1, (double)step));
-    a.bias_corr2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
     a.max_norm = max_norm;
     a.sumsq = sumsq_dev;
     a.lr_wd = (float)(lr * weight_decay);
     a.b1 = (float)beta1; a.one_minus_b1 = (float)(1.0 - beta1);
     a.b2 = (float)beta2; a.one_minus_b2 = (float)(1.0 - beta2);
     a.eps_f = (float)eps;
-    a.step_size = (float)(lr / (double)a.bias_corr1);
     cudaStream_t s = (cudaStream_t)stream;
     pre_launch(ctx, TAG_OPTIMIZER, s);
     static const bool f64_math = getenv("JAT_ADAMW_F64") && atoi(getenv("JAT_ADAMW_F64")) != 0;  // ATen's operand types

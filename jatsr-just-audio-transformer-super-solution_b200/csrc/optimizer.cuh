@@ -26,6 +26,8 @@ struct OptTensor {  // mirrors jat_adamw_tensor (include/jat_b200.h)
     long long numel;
     int packed_dtype;   // JAT_DTYPE_BF16 / JAT_DTYPE_F32
     int vec_ok;         // every pointer 16-byte aligned and numel % 4 == 0
+    float bias_corr1;       // 1 - beta1^step of THIS tensor (parameters may have been frozen for some steps)
+    float bias_corr2_sqrt;  // sqrt(1 - beta2^step)
 };
 
 __device__ __forceinline__ int opt_find_tensor(const int* __restrict__ chunk_first, int n_tensors, int chunk) {
@@ -93,12 +95,10 @@ grad_sumsq_final_kernel(const float* __restrict__ partials, int n, double* __res
 
 struct AdamWArgs {
     double lr, beta1, beta2, eps, weight_decay;
-    float bias_corr1;       // 1 - beta1^step
-    float bias_corr2_sqrt;  // sqrt(1 - beta2^step)
     float max_norm;         // <= 0: no clipping
     const double* sumsq;    // ||g||^2 over ALL tensors that are clipped together (device), or NULL
     // f32 images of the coefficients, each rounded once from its f64 value on the host
-    float lr_wd, b1, one_minus_b1, b2, one_minus_b2, eps_f, step_size;
+    float lr_wd, b1, one_minus_b1, b2, one_minus_b2, eps_f;
 };
 
 // AdamW (ATen fused_adam_utils.cuh adam_math, ADAMW mode, no amsgrad / maximize / grad scaler).
@@ -107,20 +107,21 @@ struct AdamWArgs {
 //           moment updates round once from f64).  Measured on B200 at 763 M parameters: 6.8 ms vs 3.5 ms -- the f64 /
 //           conversion pipes, not HBM, bound that form (torch's own fused AdamW: 4.7 ms).
 template <int F64>
-__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWArgs& a, float clip) {
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWArgs& a, float clip, float step_size,
+                                          float bc2_sqrt) {
     g *= clip;
     if constexpr (F64) {
         p = (float)((double)p - a.lr * a.weight_decay * (double)p);
         m = (float)(a.beta1 * (double)m + (1.0 - a.beta1) * (double)g);
         v = (float)(a.beta2 * (double)v + (1.0 - a.beta2) * (double)g * (double)g);
-        const float denom = (float)((double)(sqrtf(v) / a.bias_corr2_sqrt) + a.eps);
-        p -= a.step_size * m / denom;
+        const float denom = (float)((double)(sqrtf(v) / bc2_sqrt) + a.eps);
+        p -= step_size * m / denom;
     } else {
         p -= a.lr_wd * p;
         m = a.b1 * m + a.one_minus_b1 * g;
         v = a.b2 * v + a.one_minus_b2 * g * g;
-        const float denom = sqrtf(v) / a.bias_corr2_sqrt + a.eps_f;
-        p -= a.step_size * m / denom;
+        const float denom = sqrtf(v) / bc2_sqrt + a.eps_f;
+        p -= step_size * m / denom;
     }
 }
 
@@ -138,6 +139,7 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
         const float c = a.max_norm / (total + 1e-6f);    // torch.nn.utils.clip_grad_norm_
         clip = c < 1.0f ? c : 1.0f;
     }
+    const float step_size = (float)(a.lr / (double)t.bias_corr1);
     if (t.vec_ok) {
         constexpr int NV = OPT_CHUNK / 4 / OPT_THREADS;
         float4* p4 = reinterpret_cast<float4*>(t.param + e0);
@@ -154,10 +156,10 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
         for (int i = 0; i < NV; ++i) {
             const int q = i * OPT_THREADS + threadIdx.x;
             if (q * 4 >= n) continue;
-            adamw_one<F64>(p[i].x, g[i].x, m[i].x, v[i].x, a, clip);
-            adamw_one<F64>(p[i].y, g[i].y, m[i].y, v[i].y, a, clip);
-            adamw_one<F64>(p[i].z, g[i].z, m[i].z, v[i].z, a, clip);
-            adamw_one<F64>(p[i].w, g[i].w, m[i].w, v[i].w, a, clip);
+            adamw_one<F64>(p[i].x, g[i].x, m[i].x, v[i].x, a, clip, step_size, t.bias_corr2_sqrt);
+            adamw_one<F64>(p[i].y, g[i].y, m[i].y, v[i].y, a, clip, step_size, t.bias_corr2_sqrt);
+            adamw_one<F64>(p[i].z, g[i].z, m[i].z, v[i].z, a, clip, step_size, t.bias_corr2_sqrt);
+            adamw_one<F64>(p[i].w, g[i].w, m[i].w, v[i].w, a, clip, step_size, t.bias_corr2_sqrt);
             __stcs(p4 + q, p[i]); __stcs(m4 + q, m[i]); __stcs(v4 + q, v[i]);
             if (t.packed != nullptr) {
                 if (t.packed_dtype == 1)   // JAT_DTYPE_BF16: stays in L2 for the next forward where it fits
@@ -170,7 +172,7 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
     } else {
         for (long long i = threadIdx.x; i < n; i += OPT_THREADS) {
             float p = t.param[e0 + i], m = t.exp_avg[e0 + i], v = t.exp_avg_sq[e0 + i];
-            adamw_one<F64>(p, t.grad[e0 + i], m, v, a, clip);
+            adamw_one<F64>(p, t.grad[e0 + i], m, v, a, clip, step_size, t.bias_corr2_sqrt);
             t.param[e0 + i] = p; t.exp_avg[e0 + i] = m; t.exp_avg_sq[e0 + i] = v;
             if (t.packed != nullptr) {
                 if (t.packed_dtype == 1) reinterpret_cast<__nv_bfloat16*>(t.packed)[e0 + i] = __float2bfloat16_rn(p);

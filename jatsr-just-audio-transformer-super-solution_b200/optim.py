@@ -32,11 +32,11 @@ class _Group:
             total += (p.numel() + chunk - 1) // chunk
         self.n, self.total_chunks = n, total
         self.chunk_first = torch.tensor(first, dtype=torch.int32).to(device)
-        self.table = torch.zeros(n, 7, dtype=torch.int64, device=device)
+        self.table = torch.zeros(n, 8, dtype=torch.int64, device=device)
         self.partials = torch.empty(total, dtype=torch.float32, device=device)
         dsts = [packed_of.get(id(p)) for p in params]
         rows = [[p.data_ptr(), 0, states[p]["exp_avg"].data_ptr(), states[p]["exp_avg_sq"].data_ptr(),
-                 d.data_ptr() if d is not None else 0, p.numel(), 0] for p, d in zip(params, dsts)]
+                 d.data_ptr() if d is not None else 0, p.numel(), 0, 0] for p, d in zip(params, dsts)]
         self.static = torch.tensor(rows, dtype=torch.int64)
         self.static_ok = torch.tensor([all(r[j] % 16 == 0 for j in (0, 2, 3, 4)) and r[5] % 4 == 0 for r in rows])
         self.dtype_bits = torch.tensor([1 if (d is not None and d.dtype == torch.bfloat16) else 0 for d in dsts],
@@ -46,13 +46,17 @@ class _Group:
     def _key(self, states):
         return tuple((p.data_ptr(), states[p]["exp_avg"].data_ptr(), states[p]["exp_avg_sq"].data_ptr()) for p in self.params)
 
-    def upload(self):
-        """Gradient pointers change from step to step (autograd hands out fresh tensors): column 1 + the vec_ok flag.
+    def upload(self, steps, beta1, beta2):
+        """Gradient pointers change from step to step (autograd hands out fresh tensors): column 1 + the vec_ok flag; the
+        bias corrections follow each tensor's own step count (torch/optim/adam.py keeps `step` per parameter).
         A fresh pageable host tensor per step: the driver stages it at call time, so the host may run ahead of the stream."""
         g = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
         h = self.static.clone()
         h[:, 1] = g
         h[:, 6] = self.dtype_bits | ((self.static_ok & (g % 16 == 0)).to(torch.int64) << 32)
+        st = torch.stack(steps).to(torch.float64)
+        bc = torch.stack([1.0 - beta1 ** st, torch.sqrt(1.0 - beta2 ** st)], 1).to(torch.float32).contiguous()
+        h[:, 7] = bc.view(torch.int64).reshape(-1)      # two packed f32: bias_corr1 | bias_corr2_sqrt
         self.table.copy_(h, non_blocking=True)
 
 
@@ -102,6 +106,8 @@ class FusedAdamW(torch.optim.AdamW):
                 if p.dtype != torch.float32 or not p.is_contiguous() or p.device != device or p.grad.is_sparse:
                     raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: parameters must be f32, contiguous, dense and on one CUDA device")
                 self._ensure_state(p)
+                if self.state[p]["step"].device.type != "cpu":   # e.g. a checkpoint written by torch's fused / capturable AdamW
+                    self.state[p]["step"] = self.state[p]["step"].detach().to("cpu", torch.float32)
                 if self.state[p]["exp_avg"].device != device:  # state loaded from a checkpoint on another device
                     for k in ("exp_avg", "exp_avg_sq"):
                         self.state[p][k] = self.state[p][k].to(device)
@@ -141,8 +147,14 @@ class FusedAdamW(torch.optim.AdamW):
         lib, ctx, stream = L.load(), L.context(device.index if device.index is not None else torch.cuda.current_device()), \
             _stream(device)
         live = [g for g in self._groups if g is not None]
-        for g in live:
-            g.upload()
+        for group, g in zip(self.param_groups, self._groups):
+            if g is None:
+                continue
+            if group.get("amsgrad") or group.get("maximize"):
+                raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: amsgrad / maximize are not supported")
+            steps = [self.state[p]["step"] for p in g.params]
+            torch._foreach_add_(steps, 1)          # host tensors: no device sync
+            g.upload(steps, *group["betas"])
         clip = self.max_grad_norm is not None
         if clip:
             for j, g in enumerate(live):
@@ -152,16 +164,11 @@ class FusedAdamW(torch.optim.AdamW):
         for group, g in zip(self.param_groups, self._groups):
             if g is None:
                 continue
-            if group.get("amsgrad") or group.get("maximize"):
-                raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: amsgrad / maximize are not supported")
-            steps = [self.state[p]["step"] for p in g.params]
-            torch._foreach_add_(steps, 1)
-            step = int(steps[0].item())   # host tensor: no device sync
             b1, b2 = group["betas"]
             lr = group["lr"]
             L.check(lib.jat_adamw_step(ctx, g.table.data_ptr(), g.chunk_first.data_ptr(), g.n, g.total_chunks,
                                        float(lr), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                                       step, float(self.max_grad_norm) if clip else 0.0,
+                                       float(self.max_grad_norm) if clip else 0.0,
                                        self._sumsq.data_ptr() if clip else None, stream))
         # the kernels wrote through raw pointers: tell autograd / the engine that the parameters changed ...
         torch.autograd.graph.increment_version([p for g in live for p in g.params])

@@ -137,3 +137,50 @@ def test_fused_adamw_refreshes_the_packed_weights_of_the_drop_in_module():
     num = sum(float(((p - q) ** 2).sum()) for p, q in zip(model.parameters(), twin.parameters()))
     den = sum(float((q ** 2).sum()) for q in twin.parameters())
     assert (num / den) ** 0.5 < 2e-3   # two bf16-forward training runs, 6 steps apart from round-off in the gradients
+
+
+def test_fused_adamw_param_groups_share_one_clip_norm():
+    """Two parameter groups (no weight decay on the 1-D tensors, another lr): one norm over both, per-group hyper-parameters,
+    lr changed between steps as a scheduler would."""
+    import jat_b200
+    g = torch.Generator(device=dev()).manual_seed(7)
+    mine = [torch.nn.Parameter(torch.randn(s, generator=g, device=dev())) for s in SHAPES]
+    ref = _clone_params(mine)
+
+    def groups(ps):
+        return [dict(params=[p for p in ps if p.dim() > 1], weight_decay=0.1),
+                dict(params=[p for p in ps if p.dim() <= 1], weight_decay=0.0, lr=5e-3)]
+    opt = jat_b200.FusedAdamW(groups(mine), lr=1e-3, max_grad_norm=0.5)
+    ropt = torch.optim.AdamW(groups(ref), lr=1e-3)
+    for step in range(4):
+        for o in (opt, ropt):
+            o.param_groups[0]["lr"] = 1e-3 * (step + 1) / 4            # warm-up, train_ddp_v3mod2.py:712-717
+        for p, q in zip(mine, ref):
+            gr = torch.randn(p.shape, generator=g, device=dev())
+            p.grad, q.grad = gr.clone(), gr.clone()
+        want_norm = torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        ropt.step()
+        opt.step()
+        assert abs(float(opt.grad_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
+        for i, (p, q) in enumerate(zip(mine, ref)):
+            _close(p.detach(), q.detach(), ("param", step, i))
+
+
+def test_fused_adamw_skips_parameters_without_gradient():
+    import jat_b200
+    g = torch.Generator(device=dev()).manual_seed(8)
+    mine = [torch.nn.Parameter(torch.randn(s, generator=g, device=dev())) for s in SHAPES[:4]]
+    ref = _clone_params(mine)
+    opt, ropt = jat_b200.FusedAdamW(mine, lr=1e-2), torch.optim.AdamW(ref, lr=1e-2)
+    for step in range(3):
+        for i, (p, q) in enumerate(zip(mine, ref)):
+            if i == 1 and step < 2:          # frozen for the first two steps
+                p.grad = q.grad = None
+                continue
+            gr = torch.randn(p.shape, generator=g, device=dev())
+            p.grad, q.grad = gr.clone(), gr.clone()
+        ropt.step()
+        opt.step()
+        for p, q in zip(mine, ref):
+            _close(p.detach(), q.detach(), ("param", step))
+    assert float(opt.state[mine[1]]["step"]) == 1.0 and float(opt.state[mine[0]]["step"]) == 3.0

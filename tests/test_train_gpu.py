@@ -106,6 +106,39 @@ def test_training_step_runs_under_optimizer_and_is_repeatable(opt_kind):
     assert abs(e - losses[-1]) < 1e-3 * max(1.0, losses[-1])
 
 
+def test_gradient_accumulation_over_two_backward_passes():
+    """Two micro-batches without zero_grad in between: p.grad holds the sum (the packed gradient buffers are re-used by every
+    backward, so what autograd accumulates must be a copy), and the forward in between sees unchanged weights."""
+    import jat_b200
+    cfg = dict(input_channels=32, cond_channels=32, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
+               bottleneck_dim=128, mlp_ratio=2.0, dropout=0.0, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    model = jat_b200.JaT_AudioSR_V2(**cfg).to(dev()).train()
+    g = torch.Generator(device=dev()).manual_seed(4)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "adaLN_modulation.1" in n or n.startswith("final_layer.1"):
+                p.copy_(torch.randn(p.shape, generator=g, device=dev()) * 0.02)
+    B, T = 3, 86
+    batches = []
+    for _ in range(2):
+        hr, lr, eps = (torch.randn(B, 32, T, generator=g, device=dev()) for _ in range(3))
+        t = torch.rand(B, generator=g, device=dev())
+        batches.append((t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * eps, t, lr, hr))
+
+    def grad_of(batch):
+        model.zero_grad(set_to_none=True)
+        z, t, lr, hr = batch
+        torch.nn.functional.mse_loss(model(z, t, lr), hr).backward()
+        return [p.grad.clone() for p in model.parameters()]
+    g0, g1 = grad_of(batches[0]), grad_of(batches[1])
+    model.zero_grad(set_to_none=True)
+    for z, t, lr, hr in batches:
+        torch.nn.functional.mse_loss(model(z, t, lr), hr).backward()
+    for p, a, b in zip(model.parameters(), g0, g1):
+        assert rel_l2((a + b).cpu().numpy(), p.grad.cpu().numpy()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ f2: fused step glue
 @pytest.mark.parametrize("shape", [(3, 64, 1378), (2, 8, 87)])
 @pytest.mark.parametrize("variant", ["v3mod2", "v3m2_cfg_dropout", "adaptive", "plain"])
