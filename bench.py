@@ -354,6 +354,7 @@ def train_main(a, K, W, rank, world, local):
             if "adaLN_modulation.1" in name or name.startswith("final_layer.1"):
                 p.copy_(torch.randn(p.shape, generator=g, device=dev) * 0.02)
     model.train()
+    model.grad_handoff = os.environ.get("JAT_GRAD_HANDOFF", "view")   # zero-copy .grad (the step calls zero_grad(set_to_none=True))
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(
@@ -435,7 +436,7 @@ def train_main(a, K, W, rank, world, local):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "configs[3]: v3mod2 DiT 1280/28/20Q/4KV training step, batch 28 x [1024,1378] per GPU "
                                        "(9660 token rows): normalise + cond-noise + flow-matching mix, forward (Dropout 0.1, DropPath 0.05), "
-                                       "MSE x-prediction loss, backward, clip_grad_norm_(1.0) + AdamW + bf16 weight re-pack "
+                                       "MSE x-prediction loss, backward (grad_handoff=" + model.grad_handoff + "), clip_grad_norm_(1.0) + AdamW + bf16 weight re-pack "
                                        + ("(jat_b200.FusedAdamW: 2 multi-tensor passes)" if fused_opt else "(torch: foreach clip, fused AdamW, re-cast)"),
                            "norm": a.norm, "dropout": cfg["dropout"], "drop_path": cfg["drop_path_rate"],
                            "cond_noise_ratio": 0.05,

@@ -52,19 +52,32 @@ class _Stage(torch.autograd.Function):
     def backward(ctx, grad):
         model, (B, T, dev) = ctx.model, ctx.shape
         eng = model._engine
+        need = [p for p in ctx.params if p.requires_grad]
+        view_mode = model.grad_handoff == "view"
+        if view_mode:
+            packed = eng.grads(dev).by_param
+            for p in need:  # a live .grad that IS the packed buffer would be overwritten (and then added to itself)
+                if p.grad is not None and p.grad.data_ptr() == packed[p].data_ptr():
+                    raise L.JatError(L.ERR_BAD_ARG, "grad_handoff='view': a parameter's .grad from the previous backward is still "
+                                     "alive; call zero_grad(set_to_none=True) before every backward (no gradient accumulation), "
+                                     "or use grad_handoff='copy'")
         if ctx.kind == "final":
             by_param = eng.backward_begin(grad.float().contiguous(), B, T)
         elif ctx.kind == "block":
             by_param = eng.backward_block(ctx.index, B, T, dev)
         else:
             by_param = eng.backward_end(B, T, dev)
-        # fresh tensors: autograd / DDP keep (or accumulate into) what is returned, the packed buffers are reused.
-        # One flat allocation + one multi-tensor copy per stage instead of a clone per parameter.
-        need = [p for p in ctx.params if p.requires_grad]
-        flat = torch.empty(sum(p.numel() for p in need), dtype=torch.float32, device=dev)
-        outs = [v.view(p.shape) for v, p in zip(flat.split([p.numel() for p in need]), need)]
-        if outs:
-            torch._foreach_copy_(outs, [by_param[p] for p in need])
+        if view_mode:
+            # zero-copy hand-off: fresh view objects of the packed gradient buffers (autograd adopts them as .grad; DDP copies
+            # them into its buckets).  Valid until the next backward pass re-uses the buffers.
+            outs = [by_param[p].view(p.shape) for p in need]
+        else:
+            # fresh tensors: autograd / DDP keep (or accumulate into) what is returned, the packed buffers are reused.
+            # One flat allocation + one multi-tensor copy per stage instead of a clone per parameter.
+            flat = torch.empty(sum(p.numel() for p in need), dtype=torch.float32, device=dev)
+            outs = [v.view(p.shape) for v, p in zip(flat.split([p.numel() for p in need]), need)]
+            if outs:
+                torch._foreach_copy_(outs, [by_param[p] for p in need])
         it = iter(outs)
         grads = tuple(next(it) if p.requires_grad else None for p in ctx.params)
         tok = None if ctx.kind == "embed" else torch.zeros(1, device=dev)
@@ -179,6 +192,12 @@ class _JaTBase(nn.Module):
         self.final_layer = nn.Sequential(fin_norm, nn.Linear(hidden_size, patch_len * input_channels))
         self.initialize_weights()
         object.__setattr__(self, "_engine", Engine(self))  # not a submodule / not in state_dict
+        # How parameter gradients leave the backward pass.  "copy" (default): fresh tensors, ordinary autograd semantics
+        # (accumulation over several backward passes, zero_grad(set_to_none=False), .grad kept across steps).  "view": the
+        # .grad tensors are views of the library's packed gradient buffers (no 3 GB copy per step); they are valid until the
+        # next backward pass, which requires zero_grad(set_to_none=True) before every backward (checked) -- or DDP with
+        # gradient_as_bucket_view=True, which moves them into its buckets right away.
+        object.__setattr__(self, "grad_handoff", "copy")
 
     def initialize_weights(self):
         """adaLN-Zero: zero the modulation and final projections (jat_audiosr_v2.py:372-381)."""

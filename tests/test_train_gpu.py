@@ -139,6 +139,51 @@ def test_gradient_accumulation_over_two_backward_passes():
         assert rel_l2((a + b).cpu().numpy(), p.grad.cpu().numpy()) < 1e-5
 
 
+def test_zero_copy_gradient_handoff_matches_copy_and_guards_against_aliasing():
+    """grad_handoff='view': .grad tensors are views of the packed gradient buffers -- same values as the default copy mode,
+    an optimizer loop with zero_grad(set_to_none=True) trains identically, and a backward pass that would overwrite a live
+    .grad (gradient accumulation / set_to_none=False) raises instead of corrupting it."""
+    import jat_b200
+    from jat_b200 import _lib as L
+    cfg = dict(input_channels=32, cond_channels=32, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
+               bottleneck_dim=128, mlp_ratio=2.0, dropout=0.0, drop_path_rate=0.0)
+    g = torch.Generator(device=dev()).manual_seed(5)
+    B, T = 3, 86
+    hr, lr, eps = (torch.randn(B, 32, T, generator=g, device=dev()) for _ in range(3))
+    t = torch.rand(B, generator=g, device=dev())
+    z_t = t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * eps
+    models = []
+    for mode in ("copy", "view"):
+        torch.manual_seed(0)
+        m = jat_b200.JaT_AudioSR_V3(**cfg).to(dev()).train()
+        gi = torch.Generator(device=dev()).manual_seed(9)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "adaLN_modulation.1" in n or n.startswith("final_layer.1"):
+                    p.copy_(torch.randn(p.shape, generator=gi, device=dev()) * 0.02)
+        m.grad_handoff = mode
+        models.append(m)
+    opts = [jat_b200.FusedAdamW(m.parameters(), lr=2e-3, weight_decay=0.1, max_grad_norm=1.0, model=m) for m in models]
+    for step in range(4):
+        losses = []
+        for m, o in zip(models, opts):
+            o.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(m(z_t, t, lr), hr)
+            loss.backward()
+            losses.append(loss.item())
+        for p, q in zip(models[0].parameters(), models[1].parameters()):
+            assert rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-5   # f32 atomics in the column sums only
+        packed = models[1]._engine.grads(dev()).by_param
+        assert all(q.grad.data_ptr() == packed[q].data_ptr() for q in models[1].parameters())   # really zero-copy
+        assert abs(losses[0] - losses[1]) <= 1e-4 * max(1.0, losses[0])
+        for o in opts:
+            o.step()
+    with pytest.raises(L.JatError):   # .grad still alive: the next backward would overwrite it
+        torch.nn.functional.mse_loss(models[1](z_t, t, lr), hr).backward()
+    models[1].zero_grad(set_to_none=True)
+    torch.nn.functional.mse_loss(models[1](z_t, t, lr), hr).backward()       # fine again
+
+
 # ------------------------------------------------------------------------------------------------ f2: fused step glue
 @pytest.mark.parametrize("shape", [(3, 64, 1378), (2, 8, 87)])
 @pytest.mark.parametrize("variant", ["v3mod2", "v3m2_cfg_dropout", "adaptive", "plain"])
