@@ -23,8 +23,11 @@ adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restric
                            float2* __restrict__ rowstats, float* __restrict__ x_copy) {
     // rowstats / x_copy (training forward, optional): the row's (mean, rstd) and an f32 copy of the row, kept for the backward
     pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
-    const int row = blockIdx.x * ADALN_WARPS + (threadIdx.x >> 5);
-    if (row >= M) return;
+    // Rows are visited from the LAST to the first: the GEMM that produced x wrote its row blocks in ascending order, so the
+    // highest rows are the ones still in L2; and the GEMM that consumes `out` starts at row block 0, i.e. at the rows this
+    // grid writes last.
+    const int row = M - 1 - (int)(blockIdx.x * ADALN_WARPS + (threadIdx.x >> 5));
+    if (row < 0) return;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
