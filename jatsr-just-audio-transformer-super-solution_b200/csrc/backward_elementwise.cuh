@@ -243,7 +243,7 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
     __shared__ float4 red[2][16][2];  // [buffer][warp][sum g | sum g xhat] for the R rows of a group
     const int c4 = threadIdx.x, lane = c4 & 31, warp = c4 >> 5, nw = (int)(blockDim.x >> 5);
     const bool act = c4 < (D >> 2);
-    const int b = blockIdx.y;
+    const int b = (int)(gridDim.y - 1 - blockIdx.y);  // last rows first: dh / dx were written in ascending row order, dy is consumed from row 0
     const float inv_d = 1.0f / (float)D;
     float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), w4 = sc4, g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 1.0f;
@@ -259,7 +259,7 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a_shift = zero4, a_scale = zero4, a_w = zero4, a_gate = zero4, a_sum = zero4;
-    const int n0 = blockIdx.x * rows_per_cta;
+    const int n0 = (int)(gridDim.x - 1 - blockIdx.x) * rows_per_cta;
     const int n1 = min(n0 + rows_per_cta, tokens_per_batch);
     const long long row0 = (long long)b * tokens_per_batch;
     int buf = 0;
