@@ -66,9 +66,15 @@ def ncu_traffic(kernel_class):
     """DRAM bytes per launch of a kernel class from the committed ncu `--set full` capture (None if absent)."""
     import re
     epi = {"gemm_bias_act": 0, "gemm_qkv_rope": 1, "gemm_gate_residual": 2, "gemm_unpatchify": 3}
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1b_ncu_full_summary.json")))
-    except Exception:
+    d = None
+    for tag in ("r1c", "r1b"):   # latest committed capture first
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.json")))
+            ncu_traffic.source = f"profiles/{tag}_ncu_full_summary.json"
+            break
+        except Exception:
+            continue
+    if d is None:
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     vals = []
@@ -279,7 +285,7 @@ def main():
     roof = {k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
     roof.update(kernel=top, peak_source=f"MEASURED_PEAKS.json sustained ({pkz['src']})", traffic=ncu_traffic(top),
                 share_of_step=kernels[top]["share"])
-    roof["traffic_source"] = ("profiles/r1b_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum per launch "
+    roof["traffic_source"] = (getattr(ncu_traffic, "source", "profiles/") + ": dram__bytes_read.sum + dram__bytes_write.sum per launch "
                               "(ncu --set full, cold cache), mean over the launches of this class in the capture")
 
     # ---- e2e through the public sampler API with host buffers
