@@ -7,8 +7,8 @@
 It IS a `torch.optim.AdamW`: same constructor, same `param_groups` (lr schedulers work), same `state` / `state_dict()`
 layout (`step`, `exp_avg`, `exp_avg_sq` per parameter), so the reference's checkpoints load into it and its checkpoints
 load into the stock optimizer.  Only `step()` differs: `jat_grad_sumsq` (one read of the gradients -> ||g||^2 on the
-device) and `jat_adamw_step` (one pass: clip coefficient applied on the fly, decoupled decay, Adam update with ATen's
-operand types, packed copy written in the same pass).  There is no host synchronisation and no CPU fallback.
+device) and `jat_adamw_step` (one pass: clip coefficient applied on the fly, decoupled decay, Adam update in ATen's
+operation order, packed copy written in the same pass).  There is no host synchronisation and no CPU fallback.
 """
 from __future__ import annotations
 
@@ -42,22 +42,32 @@ class _Group:
         self.dtype_bits = torch.tensor([1 if (d is not None and d.dtype == torch.bfloat16) else 0 for d in dsts],
                                        dtype=torch.int64)
         self.key = self._key(states)
+        # two pinned staging buffers used alternately, each guarded by an event: the host may run a step ahead of the stream
+        self.host = [torch.empty(n, 8, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.done = [None, None]
+        self.turn = 0
 
     def _key(self, states):
         return tuple((p.data_ptr(), states[p]["exp_avg"].data_ptr(), states[p]["exp_avg_sq"].data_ptr()) for p in self.params)
 
     def upload(self, steps, beta1, beta2):
         """Gradient pointers change from step to step (autograd hands out fresh tensors): column 1 + the vec_ok flag; the
-        bias corrections follow each tensor's own step count (torch/optim/adam.py keeps `step` per parameter).
-        A fresh pageable host tensor per step: the driver stages it at call time, so the host may run ahead of the stream."""
+        bias corrections follow each tensor's own step count (torch/optim/adam.py keeps `step` per parameter)."""
         g = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
-        h = self.static.clone()
+        k = self.turn
+        self.turn ^= 1
+        if self.done[k] is not None:
+            self.done[k].synchronize()      # the copy issued two steps ago has long finished; wait if it has not
+        h = self.host[k]
+        h.copy_(self.static)
         h[:, 1] = g
         h[:, 6] = self.dtype_bits | ((self.static_ok & (g % 16 == 0)).to(torch.int64) << 32)
         st = torch.stack(steps).to(torch.float64)
         bc = torch.stack([1.0 - beta1 ** st, torch.sqrt(1.0 - beta2 ** st)], 1).to(torch.float32).contiguous()
         h[:, 7] = bc.view(torch.int64).reshape(-1)      # two packed f32: bias_corr1 | bias_corr2_sqrt
         self.table.copy_(h, non_blocking=True)
+        self.done[k] = torch.cuda.Event()
+        self.done[k].record(torch.cuda.current_stream(self.table.device))
 
 
 class FusedAdamW(torch.optim.AdamW):
