@@ -134,8 +134,8 @@ def test_fused_adamw_refreshes_the_packed_weights_of_the_drop_in_module():
     assert losses[-1][0] < 0.95 * losses[0][0], losses
     for l_mine, l_ref in losses:
         assert abs(l_mine - l_ref) <= 2e-3 * max(1.0, l_ref), losses
-    num = sum(float(((p - q) ** 2).sum()) for p, q in zip(model.parameters(), twin.parameters()))
-    den = sum(float((q ** 2).sum()) for q in twin.parameters())
+    num = sum(float(((p.detach() - q.detach()) ** 2).sum()) for p, q in zip(model.parameters(), twin.parameters()))
+    den = sum(float((q.detach() ** 2).sum()) for q in twin.parameters())
     assert (num / den) ** 0.5 < 2e-3   # two bf16-forward training runs, 6 steps apart from round-off in the gradients
 
 
@@ -184,3 +184,54 @@ def test_fused_adamw_skips_parameters_without_gradient():
         for p, q in zip(mine, ref):
             _close(p.detach(), q.detach(), ("param", step))
     assert float(opt.state[mine[1]]["step"]) == 1.0 and float(opt.state[mine[0]]["step"]) == 3.0
+
+
+@pytest.mark.parametrize("handoff", ["copy", "view"])
+def test_grad_scaler_loop_as_in_the_reference(handoff):
+    """The reference's step (train_ddp_v3mod2.py:922-930): scaler.scale(loss).backward(); scaler.unscale_(optimizer);
+    clip_grad_norm_; scaler.step(optimizer); scaler.update() -- with FusedAdamW in place of AdamW + clip, against the stock
+    sequence on a twin model.  An overflowing step (inf in the loss scale path) must be skipped by both."""
+    import jat_b200
+    cfg = dict(input_channels=32, cond_channels=32, patch_len=4, hidden_size=128, depth=2, num_q_heads=2, num_kv_heads=1,
+               bottleneck_dim=128, mlp_ratio=2.0, dropout=0.0, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    model = jat_b200.JaT_AudioSR_V2(**cfg).to(dev()).train()
+    g = torch.Generator(device=dev()).manual_seed(3)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "adaLN_modulation.1" in n or n.startswith("final_layer.1"):
+                p.copy_(torch.randn(p.shape, generator=g, device=dev()) * 0.02)
+    twin = jat_b200.JaT_AudioSR_V2(**cfg).to(dev()).train()
+    twin.load_state_dict(model.state_dict())
+    model.grad_handoff = handoff
+    B, T = 4, 86
+    hr, lr, eps = (torch.randn(B, 32, T, generator=g, device=dev()) for _ in range(3))
+    t = torch.rand(B, generator=g, device=dev())
+    z_t = t.view(B, 1, 1) * hr + (1 - t.view(B, 1, 1)) * eps
+    kw = dict(lr=2e-3, weight_decay=0.1)
+    opt = jat_b200.FusedAdamW(model.parameters(), max_grad_norm=1.0, model=model, **kw)
+    ropt = torch.optim.AdamW(twin.parameters(), **kw)
+    sc, rsc = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for step in range(5):
+        poison = float("inf") if step == 2 else 1.0          # one overflowing step: both scalers must skip it
+        opt.zero_grad(set_to_none=True)
+        ropt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(z_t, t, lr), hr) * poison
+        sc.scale(loss).backward()
+        sc.unscale_(opt)
+        sc.step(opt)
+        sc.update()
+        rloss = torch.nn.functional.mse_loss(twin(z_t, t, lr), hr) * poison
+        rsc.scale(rloss).backward()
+        rsc.unscale_(ropt)
+        torch.nn.utils.clip_grad_norm_(twin.parameters(), 1.0)
+        rsc.step(ropt)
+        rsc.update()
+        assert sc.get_scale() == rsc.get_scale()
+        if step != 2:
+            assert abs(loss.item() - rloss.item()) <= 2e-3 * max(1.0, rloss.item())
+    assert sc.get_scale() == 512.0                            # halved once by the skipped step
+    num = sum(float(((p.detach() - q.detach()) ** 2).sum()) for p, q in zip(model.parameters(), twin.parameters()))
+    den = sum(float((q.detach() ** 2).sum()) for q in twin.parameters())
+    assert (num / den) ** 0.5 < 2e-3
+    assert float(opt.state[next(iter(model.parameters()))]["step"]) == 4.0   # 5 iterations, one skipped
