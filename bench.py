@@ -345,7 +345,13 @@ def train_main(a, K, W, rank, world, local):
     from jat_b200 import _lib as L
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", init_method="env://")
+        # NCCL kernels on a high-priority stream: they get SMs at the next kernel boundary instead of queueing behind the
+        # library's persistent GEMM grids (4 GPUs: 57.4 -> 56.1 ms / step); JAT_NCCL_HIPRI=0 = torch's default
+        if os.environ.get("JAT_NCCL_HIPRI", "1") == "1":
+            dist.init_process_group("nccl", init_method="env://",
+                                    pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
+        else:
+            dist.init_process_group("nccl", init_method="env://")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cfg = dict(CFG)  # dropout 0.1, drop_path 0.05: the reference's training configuration (train_ddp_v3mod2.py:343-355)
@@ -446,7 +452,7 @@ def train_main(a, K, W, rank, world, local):
                                        + ("(jat_b200.FusedAdamW: 2 multi-tensor passes)" if fused_opt else "(torch: foreach clip, fused AdamW, re-cast)"),
                            "norm": a.norm, "dropout": cfg["dropout"], "drop_path": cfg["drop_path_rate"],
                            "cond_noise_ratio": 0.05,
-                           "parallelism": f"DDP x{world} (NCCL gradient all-reduce, 200 MB buckets, gradient_as_bucket_view)" if world > 1 else "single GPU"},
+                           "parallelism": f"DDP x{world} (NCCL gradient all-reduce on a high-priority stream, 200 MB buckets, gradient_as_bucket_view)" if world > 1 else "single GPU"},
                 "clocks": clk, "gpu_launches": int(launches), "loss": round(float(loss.item()), 5),
                 "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),
                 "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),

@@ -15,5 +15,5 @@ except Exception as e:
     print('N=$N $name', 'rc=$rc', 'FAILED', e)
 PY
 }
-run f32 JAT_X=0
+run ${2:-f32} ${3:-JAT_X=0}
 # (a bf16_compress_hook variant was measured once: 74.0 ms / step at 8 GPUs, slower than the f32 all-reduce)
