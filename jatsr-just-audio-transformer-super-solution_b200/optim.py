@@ -111,7 +111,7 @@ class FusedAdamW(torch.optim.AdamW):
         self._packed_seen = pk
         self._groups = []
         for group in self.param_groups:
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
             for p in params:
                 if p.dtype != torch.float32 or not p.is_contiguous() or p.device != device or p.grad.is_sparse:
                     raise L.JatError(L.ERR_BAD_ARG, "FusedAdamW: parameters must be f32, contiguous, dense and on one CUDA device")
@@ -135,7 +135,7 @@ class FusedAdamW(torch.optim.AdamW):
         if pk is not self._packed_seen:
             return False
         for group, g in zip(self.param_groups, self._groups):
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
             if (g is None) != (not params) or (g is not None and ([id(p) for p in params] != g.ids or g.key != g._key(self.state))):
                 return False
         return True
