@@ -437,6 +437,23 @@ def train_main(a, K, W, rank, world, local):
     tot = sum(v[0] for v in prof.values())
     kernels = {n: {"ms_per_step": round(v[0] / pk, 3), "launches_per_step": v[1] // pk, "share_of_kernel_time": round(v[0] / tot, 4)}
                for n, v in prof.items()}
+    # roofline of the training step's dominant kernel classes (algorithmic work of step_work() at B_eff = B; the weight-gradient
+    # GEMMs do exactly the forward GEMMs' FLOPs; the parameter update moves 30 B and the norm pass 4 B per parameter)
+    fw, _ = step_work(B)
+    fwd_gemm = sum(fw[k][1] for k in ("gemm_bias_act", "gemm_qkv_rope", "gemm_gate_residual", "gemm_unpatchify"))
+    n_params = sum(p.numel() for p in model.parameters())
+    roofs = {}
+    if "gemm_accum" in kernels:
+        tfs = fwd_gemm / (kernels["gemm_accum"]["ms_per_step"] * 1e-3) / 1e12
+        roofs["gemm_accum"] = {"bound": "tensor", "achieved": round(tfs, 1), "peak": pkz["tf"], "unit": "TFLOP/s",
+                               "frac": round(tfs / pkz["tf"], 4)}
+    if "optimizer" in kernels:
+        gbs = n_params * 34.0 / (kernels["optimizer"]["ms_per_step"] * 1e-3) / 1e9
+        roofs["optimizer"] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": pkz["hbm"], "unit": "GB/s",
+                              "frac": round(gbs / pkz["hbm"], 4)}
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    roofline = dict(roofs.get(top, {}), kernel=top, share_of_step=kernels[top]["share_of_kernel_time"],
+                    peak_source=f"MEASURED_PEAKS.json sustained ({pkz['src']})") if top in roofs else None
     # algorithmic FLOPs: forward 1023.85 MFLOP/token, backward = 2x forward, no recompute counted
     N = (T + 3) // 4
     step_flops = 3 * 1023.85e6 * B * N
@@ -456,6 +473,7 @@ def train_main(a, K, W, rank, world, local):
                 "clocks": clk, "gpu_launches": int(launches), "loss": round(float(loss.item()), 5),
                 "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),
                 "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),
+                "roofline": roofline, "rooflines": roofs,
                 "kernels": kernels, "kernel_ms_per_step": round(tot / pk, 2)}
         print(json.dumps(line), flush=True)
     if world > 1:
