@@ -68,6 +68,30 @@ def test_structs_match_header_layout(lib, tmp_path):
     assert got == want
 
 
+def test_adamw_table_entry_is_eight_int64_words(tmp_path):
+    """optim.FusedAdamW writes the device table of jat_adamw_step as an int64 [n, 8] tensor: word k of a row must be field k
+    of jat_adamw_tensor (pointers, numel, packed_dtype | vec_ok << 32, the two f32 bias corrections packed into word 7)."""
+    import subprocess
+    src = tmp_path / "opt_layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "jat_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(jat_adamw_tensor),'
+        ' offsetof(jat_adamw_tensor, param), offsetof(jat_adamw_tensor, grad), offsetof(jat_adamw_tensor, exp_avg),'
+        ' offsetof(jat_adamw_tensor, exp_avg_sq), offsetof(jat_adamw_tensor, packed), offsetof(jat_adamw_tensor, numel),'
+        ' offsetof(jat_adamw_tensor, packed_dtype), offsetof(jat_adamw_tensor, vec_ok),'
+        ' offsetof(jat_adamw_tensor, bias_corr1), offsetof(jat_adamw_tensor, bias_corr2_sqrt));return 0;}\n')
+    exe = tmp_path / "opt_layout"
+    subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [64, 0, 8, 16, 24, 32, 40, 48, 52, 56, 60]
+    # the packing of word 7 as optim._Group.upload does it: low half = bias_corr1, high half = bias_corr2_sqrt
+    bc = torch.tensor([[0.25, 0.5]], dtype=torch.float32)
+    word = int(bc.view(torch.int64).reshape(-1)[0])
+    lo = torch.tensor([word & 0xffffffff], dtype=torch.int64).to(torch.int32).view(torch.float32)
+    hi = torch.tensor([word >> 32], dtype=torch.int64).to(torch.int32).view(torch.float32)
+    assert float(lo) == 0.25 and float(hi) == 0.5
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_gpu_fails_loudly(lib):
     out = ctypes.c_void_p()
