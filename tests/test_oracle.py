@@ -215,3 +215,38 @@ def test_torch_restatement_sampler_matches_reference_sampler():
             want = ref_sampler(model, lr, num_steps=7, cfg_scale=scale, device="cpu", verbose=False)
         got = restated(sd, cfg, lr, z0, num_steps=7, cfg_scale=scale)
         assert rel_l2(got.numpy(), want.numpy()) < 1e-5, scale
+
+
+def test_optimizer_oracle_matches_torch_clip_plus_adamw():
+    """oracle/optimizer_oracle.py against what the reference's loop calls (train_ddp_v3mod2.py:709, 926-928) on CPU:
+    clip_grad_norm_(params, 1.0) + torch.optim.AdamW.step(), several steps, one parameter frozen for the first two."""
+    import torch
+    from oracle import optimizer_oracle as OO
+    rng = np.random.default_rng(0)
+    shapes = [(64, 48), (48,), (7,), (3, 5, 2)]
+    params = [torch.nn.Parameter(torch.from_numpy(rng.standard_normal(s).astype(np.float32))) for s in shapes]
+    opt = torch.optim.AdamW(params, lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, foreach=False)
+    mine = [p.detach().numpy().copy() for p in params]
+    m = [np.zeros_like(x) for x in mine]
+    v = [np.zeros_like(x) for x in mine]
+    steps = [0] * len(mine)
+    for step in range(5):
+        grads = [rng.standard_normal(s).astype(np.float32) * (5.0 if step % 2 else 0.05) for s in shapes]
+        live = [i for i in range(len(shapes)) if not (i == 1 and step < 2)]
+        for i, p in enumerate(params):
+            p.grad = torch.from_numpy(grads[i].copy()) if i in live else None
+        want_norm = float(torch.nn.utils.clip_grad_norm_(params, 1.0))
+        opt.step()
+        sub = lambda xs: [xs[i] for i in live]
+        st = [steps[i] for i in live]
+        got_norm = OO.adamw_step(sub(mine), sub(grads), sub(m), sub(v), st, lr=3e-3, betas=(0.9, 0.95), eps=1e-8,
+                                weight_decay=0.1, max_norm=1.0)
+        for k, i in enumerate(live):
+            steps[i] = st[k]
+        assert abs(got_norm - want_norm) <= 1e-5 * want_norm
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(mine[i], p.detach().numpy(), rtol=2e-6, atol=1e-6)
+            if i in live or steps[i] > 0:
+                np.testing.assert_allclose(m[i], opt.state[p]["exp_avg"].numpy(), rtol=2e-6, atol=1e-7)
+                np.testing.assert_allclose(v[i], opt.state[p]["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-7)
+    assert steps == [5, 3, 5, 5]
