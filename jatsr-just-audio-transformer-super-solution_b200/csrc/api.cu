@@ -9,7 +9,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <new>
+#include <set>
 #include <vector>
 
 #include "../../include/jat_b200.h"
@@ -50,6 +52,10 @@ struct jat_ctx {
     int tail_split;        // 0 = off; 1 = cut the tiles of a partial last wave along K, in-order fix-up (any epilogue);
                            // 2 = the same cut for the reduce-add epilogues only, parts added straight into the output
     long long* gemm_trace; // debug: device buffer of 64 x 8 clock64 slots for the GEMM kernel, or NULL
+    // function attributes are per DEVICE: which kernels already carry their dynamic shared-memory limit on ctx->device, and
+    // the co-resident cluster limit of the 4-CTA multicast GEMM instantiations there
+    std::set<const void*> smem_configured;
+    std::map<const void*, int> max_clusters;
 };
 static const size_t kTailWsBytesPerSM = 128 * 256 * sizeof(float);
 
@@ -86,12 +92,37 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (r__ != 0) return r__;  \
     } while (0)
 
+// Every launching entry point makes ctx->device current for its duration (streams, function attributes and launches are
+// per device; a process may hold one ctx per device) and restores the caller's device on return.
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(const jat_ctx* c) : prev(-1) {
+        int cur = -1;
+        if (c != nullptr && cudaGetDevice(&cur) == cudaSuccess && cur != c->device) {
+            prev = cur;
+            cudaSetDevice(c->device);
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (ctx = device, kernel)
+static int ensure_dyn_smem(jat_ctx* ctx, const void* kern, int bytes) {
+    if (ctx->smem_configured.count(kern)) return 0;
+    JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_configured.insert(kern);
+    return 0;
+}
+
 extern "C" int jat_abi_version(void) { return JAT_ABI_VERSION; }
 extern "C" const char* jat_last_error(void) { return g_err; }
 
 extern "C" int jat_create(int device, jat_ctx** out) {
     if (!out) return fail(JAT_ERR_BAD_ARG, "jat_create: out == NULL");
     *out = nullptr;
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};  // leave the caller's device current
     JAT_CUDA(cudaSetDevice(device));
     JAT_CUDA(cudaFree(0));
     cudaDeviceProp prop;
@@ -294,6 +325,7 @@ static bool make_drop(float p, uint32_t seed, DropCfg* d) {
 
 extern "C" int jat_dropout_scale_mask(jat_ctx* ctx, float* out, int64_t rows, int cols, float p, uint32_t site_seed,
                                       void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !out || rows <= 0 || cols <= 0 || rows > 0xffffffffll) return fail(JAT_ERR_BAD_ARG, "jat_dropout_scale_mask: bad argument");
     DropCfg d;
     if (!make_drop(p, site_seed, &d)) return fail(JAT_ERR_BAD_ARG, "jat_dropout_scale_mask: p must be in [0, 1)");
@@ -305,6 +337,7 @@ extern "C" int jat_dropout_scale_mask(jat_ctx* ctx, float* out, int64_t rows, in
 
 extern "C" int jat_drop_path_scales(jat_ctx* ctx, float* out, const float* rates, int depth, int B, uint64_t seed,
                                     void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !out || !rates || depth <= 0 || B <= 0) return fail(JAT_ERR_BAD_ARG, "jat_drop_path_scales: bad argument");
     const uint32_t s32 = jat_dropout_site_seed(seed, -1, JAT_DROP_SITE_PATH);
     const int n = depth * 2 * B;
@@ -319,11 +352,7 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
                        const GemmParams& p, cudaStream_t s) {
     using Cfg = GemmCfg<BN, CG>;
     auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN, MC>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        JAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    JAT_TRY(ensure_dyn_smem(ctx, (const void*)kern, Cfg::SMEM_BYTES));
     int clusters = ctx->gemm_sms / (CG * MC);
     const int num_work = p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
     if (clusters > num_work) clusters = num_work;
@@ -344,7 +373,7 @@ static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     if constexpr (MC > 1) {
         // clusters of 4 must sit inside one GPC: fewer than sm_count / 4 may be co-resident; a persistent grid larger than
         // that would run its surplus clusters as a second wave
-        static int max_clusters = -1;
+        int& max_clusters = ctx->max_clusters.emplace((const void*)kern, -1).first->second;
         if (max_clusters < 0) {
             cfg.gridDim = dim3((unsigned)(ctx->sm_count / (CG * MC) * CG * MC));
             if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) {
@@ -437,6 +466,7 @@ static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
 
 extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                              const jat_gemm_epilogue* e, int cta_pair, int block_n, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !A || !W || !e || !e->out) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: null argument");
     if (M <= 0 || N <= 0 || K <= 0) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: non-positive size");
     const bool a_mn = e->a_transposed != 0, w_mn = e->w_transposed != 0;
@@ -593,6 +623,7 @@ static int adaln_norm_modulate_stats(jat_ctx* ctx, const float* x, void* out_bf1
 extern "C" int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_bf16, const float* shift,
                                        const float* scale, int64_t mod_batch_stride, const float* weight, int norm_kind,
                                        float eps, int M, int D, int tokens_per_batch, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     return adaln_norm_modulate_stats(ctx, x, out_bf16, shift, scale, mod_batch_stride, weight, norm_kind, eps, M, D,
                                      tokens_per_batch, nullptr, nullptr, stream);
 }
@@ -623,6 +654,7 @@ static int adaln_norm_modulate_stats(jat_ctx* ctx, const float* x, void* out_bf1
 // ------------------------------------------------------------------------------------------------ misc
 extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
                                  void* out_bf16, int B, int C, int T, int P, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !x_t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_patchify_cast: null argument");
     if (P != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: patch_len must be 4 (got %d)", P);
     if (B <= 0 || C <= 0 || T <= 0 || C % PATCH_TC != 0 || xt_batch <= 0 || B > 65535)
@@ -636,6 +668,7 @@ extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, c
 }
 
 extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int C, int T, int P, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !x || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_patchify_single: null argument");
     if (P != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_single: patch_len must be 4 (got %d)", P);
     if (B <= 0 || C <= 0 || T <= 0 || C % PATCH_TC != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_single: bad sizes");
@@ -648,6 +681,7 @@ extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16,
 }
 
 extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf16, int B, int D, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_timestep_features: null argument");
     if (B <= 0 || D < 4 || D % 2 != 0 || B > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_timestep_features: bad B/D");
     dim3 grid((D / 2 + 127) / 128, B);
@@ -658,6 +692,7 @@ extern "C" int jat_timestep_features(jat_ctx* ctx, const float* t, void* out_bf1
 
 extern "C" int jat_cfg_euler_update(jat_ctx* ctx, float* z, const float* x_c, const float* x_u, float cfg_scale,
                                     const float* t_dt, int step, int64_t numel, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !z || !x_c || !t_dt) return fail(JAT_ERR_BAD_ARG, "jat_cfg_euler_update: null argument");
     if (numel <= 0 || step < 0) return fail(JAT_ERR_BAD_ARG, "jat_cfg_euler_update: bad numel/step");
     long long want = (numel / 4 + 255) / 256;
@@ -698,6 +733,7 @@ extern "C" int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, 
                              const float* weight, int norm_kind, float eps, float* dx, int accumulate, float* dshift,
                              float* dscale, int64_t dmod_batch_stride, float* dweight, float* rowstats_scratch, int B,
                              int tokens_per_batch, int D, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !dh_bf16 || !x || !dx) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: null argument");
     if (scale != nullptr && (!dshift || !dscale)) return fail(JAT_ERR_BAD_ARG, "jat_adaln_bwd: dshift/dscale missing");
     if ((scale != nullptr || dweight != nullptr) && !rowstats_scratch)
@@ -720,6 +756,7 @@ extern "C" int jat_adaln_bwd(jat_ctx* ctx, const void* dh_bf16, const float* x, 
 extern "C" int jat_gate_bwd(jat_ctx* ctx, const float* dx, const void* y_bf16, const float* gate, int64_t mod_batch_stride,
                             void* dy_bf16, float* dgate, int64_t dmod_batch_stride, float* dxsum_scratch, float* dbias, int B,
                             int tokens_per_batch, int D, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     return jat_gate_bwd_dropout(ctx, dx, y_bf16, gate, mod_batch_stride, dy_bf16, dgate, dmod_batch_stride, dxsum_scratch,
                                 dbias, B, tokens_per_batch, D, 0.0f, 0u, nullptr, stream);
 }
@@ -728,6 +765,7 @@ extern "C" int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y
                                     int64_t mod_batch_stride, void* dy_bf16, float* dgate, int64_t dmod_batch_stride,
                                     float* dxsum_scratch, float* dbias, int B, int tokens_per_batch, int D, float drop_p,
                                     uint32_t drop_seed, const float* gate_rowscale, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     DropCfg drop;
     if (!make_drop(drop_p, drop_seed, &drop)) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: drop_p must be in [0, 1)");
     if (!ctx || !dx || !y_bf16 || !gate || !dy_bf16 || !dgate) return fail(JAT_ERR_BAD_ARG, "jat_gate_bwd: null argument");
@@ -748,6 +786,7 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
                                   const float* gate, void* dy_bf16, float* dgate, float* dxsum_scratch, float* dbias, int B,
                                   int tokens_per_batch, int D, float drop_p, uint32_t drop_seed, const float* gate_rowscale,
                                   void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !dh_bf16 || !x || !rowstats || !scale || !dx || !dshift || !dscale)
         return fail(JAT_ERR_BAD_ARG, "jat_adaln_gate_bwd: null argument");
     const bool has_gate = y_bf16 != nullptr;
@@ -791,6 +830,7 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
 }
 
 extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !a_bf16 || !out) return fail(JAT_ERR_BAD_ARG, "jat_colsum_bf16: null argument");
     if (M <= 0 || cols <= 0 || cols % 4 != 0 || lda % 4 != 0 || (reinterpret_cast<uintptr_t>(a_bf16) & 7) != 0)
         return fail(JAT_ERR_BAD_SHAPE, "jat_colsum_bf16: need cols %% 4 == 0, lda %% 4 == 0, 8-byte aligned input");
@@ -804,6 +844,7 @@ extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, in
 }
 
 extern "C" int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !in || !out_bf16 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_cast_f32_bf16: bad argument");
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) != 0)
         return fail(JAT_ERR_BAD_ARG, "jat_cast_f32_bf16: misaligned");
@@ -818,6 +859,7 @@ extern "C" int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, 
                                 const float* lr_mean, const float* lr_std, const float* noise, const float* cond_noise,
                                 const float* cond_scale_dev, float cond_scale, const float* keep, const float* t, float* hr_norm,
                                 float* lr_cond, float* z_t, int B, int C, int T, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !hr || !lr || !hr_mean || !hr_std || !lr_mean || !lr_std || !noise || !t || !hr_norm || !lr_cond || !z_t)
         return fail(JAT_ERR_BAD_ARG, "jat_train_inputs: null argument");
     if (B <= 0 || C <= 0 || T <= 0 || B > 65535 || C > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_train_inputs: bad B/C/T");
@@ -833,6 +875,7 @@ extern "C" int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, 
 
 extern "C" int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n,
                             void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !pred || !target || !stats4 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: bad argument");
     if ((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)d_pred) & 15) != 0)
         return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: tensors must be 16-byte aligned");
@@ -859,6 +902,7 @@ static int opt_check(const char* fn, jat_ctx* ctx, const void* table, const void
 
 extern "C" int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
                               int total_chunks, float* partials_dev, double* sumsq_dev, int accumulate, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     JAT_TRY(opt_check("jat_grad_sumsq", ctx, table_dev, chunk_first_dev, n_tensors, total_chunks));
     if (!partials_dev || !sumsq_dev) return fail(JAT_ERR_BAD_ARG, "jat_grad_sumsq: null argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -874,6 +918,7 @@ extern "C" int jat_grad_sumsq(jat_ctx* ctx, const jat_adamw_tensor* table_dev, c
 extern "C" int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, const int32_t* chunk_first_dev, int n_tensors,
                               int total_chunks, double lr, double beta1, double beta2, double eps, double weight_decay,
                               float max_norm, const double* sumsq_dev, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     JAT_TRY(opt_check("jat_adamw_step", ctx, table_dev, chunk_first_dev, n_tensors, total_chunks));
     if (!(lr >= 0.0) || !(eps >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(weight_decay >= 0.0))
         return fail(JAT_ERR_BAD_ARG, "jat_adamw_step: hyper-parameter out of range");
@@ -898,6 +943,7 @@ extern "C" int jat_adamw_step(jat_ctx* ctx, const jat_adamw_tensor* table_dev, c
 extern "C" int jat_chunk_normalize(jat_ctx* ctx, const float* latent, int64_t total_frames, int64_t ld, const float* mean,
                                    const float* std, float* out, int n_chunks, int first_chunk, int chunk_step, int C,
                                    int chunk_frames, int stride, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !latent || !out) return fail(JAT_ERR_BAD_ARG, "jat_chunk_normalize: null argument");
     if ((mean == nullptr) != (std == nullptr)) return fail(JAT_ERR_BAD_ARG, "jat_chunk_normalize: mean and std go together");
     if (n_chunks <= 0 || C <= 0 || chunk_frames <= 0 || stride <= 0 || first_chunk < 0 || chunk_step <= 0 ||
@@ -913,6 +959,7 @@ extern "C" int jat_chunk_normalize(jat_ctx* ctx, const float* latent, int64_t to
 extern "C" int jat_crossfade_denorm(jat_ctx* ctx, const float* chunks, int n_chunks, int C, int chunk_frames, int overlap,
                                     const float* fade_in, const float* fade_out, const float* mean, const float* std,
                                     float* out, int64_t total_frames, int64_t ldo, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !chunks || !out) return fail(JAT_ERR_BAD_ARG, "jat_crossfade_denorm: null argument");
     if ((mean == nullptr) != (std == nullptr)) return fail(JAT_ERR_BAD_ARG, "jat_crossfade_denorm: mean and std go together");
     if (n_chunks <= 0 || C <= 0 || C > 65535 || chunk_frames <= 0 || overlap < 0 || total_frames <= 0 || ldo < total_frames)
@@ -940,12 +987,7 @@ static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv
     using Cfg = AttCfg<NKH>;
     CUtensorMap tkv;
     JAT_TRY(make_tmap(ctx, &tkv, qkv, rows, cols, cols, (uint32_t)NKH));
-    static bool configured = false;
-    if (!configured) {
-        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_fwd_kernel<NKH, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_fwd_kernel<NKH, DROP>, Cfg::SMEM_BYTES));
     pre_launch(ctx, TAG_ATTN, s);
     launch_pdl(gqa_attention_fwd_kernel<NKH, DROP>, grid, dim3(ATT_THREADS), Cfg::SMEM_BYTES, s, tq, tkv, p);
     return post_launch(ctx, "gqa_attention_fwd");
@@ -953,6 +995,7 @@ static int launch_attention(jat_ctx* ctx, const CUtensorMap& tq, const void* qkv
 
 extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq, int Hkv,
                                      int head_dim, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     return jat_gqa_attention_fwd_dropout(ctx, qkv, out, lse, B, N, Hq, Hkv, head_dim, 0.0f, 0u, stream);
 }
 
@@ -988,6 +1031,7 @@ static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, 
 
 extern "C" int jat_gqa_attention_fwd_dropout(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq,
                                              int Hkv, int head_dim, float drop_p, uint32_t drop_seed, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (N > ATT_MAX_NK)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: N = %d tokens > %d needs the chunked form jat_gqa_attention_fwd_long "
                     "(scratch for the per-chunk partial results)", N, ATT_MAX_NK);
@@ -999,6 +1043,7 @@ extern "C" int jat_attention_passes(int N) { return N <= 0 ? 0 : (N + ATT_MAX_NK
 extern "C" int jat_gqa_attention_fwd_long(jat_ctx* ctx, const void* qkv, void* out, float* lse, void* part_o, float* part_lse,
                                           int B, int N, int Hq, int Hkv, int head_dim, float drop_p, uint32_t drop_seed,
                                           void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !qkv || !out) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_fwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: head_dim must be 64 (got %d)", head_dim);
     if (B <= 0 || N <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || B > 65535 || Hkv > 65535)
@@ -1027,6 +1072,7 @@ extern "C" int jat_gqa_attention_fwd_long(jat_ctx* ctx, const void* qkv, void* o
 extern "C" int jat_gqa_attention_bwd(jat_ctx* ctx, const void* qkv, const void* d_out, const void* out, const float* lse,
                                      float* dsum_scratch, float* dq_acc_scratch, void* dqkv, const float* rope_cos,
                                      const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     return jat_gqa_attention_bwd_dropout(ctx, qkv, d_out, out, lse, dsum_scratch, dq_acc_scratch, dqkv, rope_cos, rope_sin, B, N,
                                          Hq, Hkv, head_dim, 0.0f, 0u, stream);
 }
@@ -1035,6 +1081,7 @@ extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, cons
                                              float* dsum_scratch, float* dq_acc_scratch, void* dqkv, const float* rope_cos,
                                              const float* rope_sin, int B, int N, int Hq, int Hkv, int head_dim, float drop_p,
                                              uint32_t drop_seed, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !qkv || !d_out || !out || !lse || !dsum_scratch || !dq_acc_scratch || !dqkv || !rope_cos || !rope_sin)
         return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: null argument");
     if (head_dim != ATT_HD) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_bwd: head_dim must be 64 (got %d)", head_dim);
@@ -1061,11 +1108,7 @@ extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, cons
     p.scale = 0.125f;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     if (!make_drop(drop_p, drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: drop_p must be in [0, 1)");
-    static bool configured = false;
-    if (!configured) {
-        JAT_CUDA(cudaFuncSetAttribute(gqa_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTB_SMEM_BYTES));
-        configured = true;
-    }
+    JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel, ATTB_SMEM_BYTES));
     dim3 grid((N + ATTB_TILE - 1) / ATTB_TILE, Hkv, B);
     pre_launch(ctx, TAG_ATTN_BWD, s);
     gqa_attention_bwd_kernel<<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
@@ -1089,6 +1132,7 @@ static jat_gemm_epilogue epi_bias_act(const float* bias, void* out, int64_t ldo,
 
 extern "C" int jat_dit_modulation(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const float* t,
                                   int Bt, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !t) return fail(JAT_ERR_BAD_ARG, "jat_dit_modulation: null argument");
     if (!ws->t_feat || !ws->t_hid || !ws->t_act || !ws->mod) return fail(JAT_ERR_BAD_ARG, "jat_dit_modulation: workspace incomplete");
     const int D = w->hidden;
@@ -1108,6 +1152,7 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
                                       const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
                                       const float* mod, int64_t mod_batch_stride, float* out, int B, int T,
                                       void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !x_t || !mod || !out) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_tokens: null argument");
     const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
     const int N = (T + P - 1) / P;
@@ -1175,6 +1220,7 @@ static char* at(void* base, int64_t index, int64_t elems, int64_t esz) { return 
 extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
                                      const jat_dit_saved* sv, const float* x_t, const float* x_cond, const float* t,
                                      float* out, int B, int T, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !sv || !x_t || !x_cond || !t || !out) return fail(JAT_ERR_BAD_ARG, "jat_dit_forward_train: null argument");
     const int D = w->hidden, P = w->patch_len, C = w->channels, F = w->mlp_hidden, BD = w->bottleneck;
     const int N = (T + P - 1) / P;
@@ -1306,6 +1352,7 @@ static BwdDims bwd_dims(const jat_dit_weights* w, int B, int T) {
 extern "C" int jat_dit_backward_begin(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
                                       const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr,
                                       const float* d_out, int B, int T, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !sv || !sc || !gr || !d_out) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_begin: null argument");
     const BwdDims d = bwd_dims(w, B, T);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1324,6 +1371,7 @@ extern "C" int jat_dit_backward_begin(jat_ctx* ctx, const jat_dit_weights* w, co
 extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
                                       const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr,
                                       int i, int B, int T, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !sv || !sc || !gr) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_block: null argument");
     if (i < 0 || i >= w->depth) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_block: block index %d out of range", i);
     const BwdDims d = bwd_dims(w, B, T);
@@ -1411,6 +1459,7 @@ extern "C" int jat_dit_backward_block(jat_ctx* ctx, const jat_dit_weights* w, co
 extern "C" int jat_dit_backward_end(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws,
                                     const jat_dit_saved* sv, const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, int B,
                                     int T, void* stream) {
+    DeviceGuard dev_guard__(ctx);
     if (!ctx || !w || !ws || !sv || !sc || !gr) return fail(JAT_ERR_BAD_ARG, "jat_dit_backward_end: null argument");
     const BwdDims d = bwd_dims(w, B, T);
     const int D = d.D, BD = d.BD, M = d.M;
@@ -1436,6 +1485,7 @@ extern "C" int jat_dit_backward_end(jat_ctx* ctx, const jat_dit_weights* w, cons
 extern "C" int jat_dit_backward(jat_ctx* ctx, const jat_dit_weights* w, const jat_dit_workspace* ws, const jat_dit_saved* sv,
                                 const jat_dit_bwd_scratch* sc, const jat_dit_weights* gr, const float* d_out, int B, int T,
                                 void* stream) {
+    DeviceGuard dev_guard__(ctx);
     JAT_TRY(jat_dit_backward_begin(ctx, w, ws, sv, sc, gr, d_out, B, T, stream));
     for (int i = w->depth - 1; i >= 0; --i) JAT_TRY(jat_dit_backward_block(ctx, w, ws, sv, sc, gr, i, B, T, stream));
     return jat_dit_backward_end(ctx, w, ws, sv, sc, gr, B, T, stream);

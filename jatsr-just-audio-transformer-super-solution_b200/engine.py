@@ -198,9 +198,14 @@ class PackedGrads:
 
 
 class TrainBuffers:
-    """Saved activations + backward scratch for one (B, T) training problem."""
+    """Saved activations + backward scratch + the activation workspace of one (B, T) training problem.  The workspace is
+    its own (not the eval path's): the backward reads mod / x / h / patches / pe_hid / t_* from it, so a no-grad forward of
+    the same shape between forward and backward (EMA / teacher / self-conditioning pass) must not touch it.  `generation`
+    identifies the forward pass whose activations the buffers currently hold."""
 
     def __init__(self, model, B, T, device):
+        self.ws = Workspace(model, B, T, B, device)
+        self.generation = 0
         D, depth = model.hidden_size, len(model.blocks)
         P, Cc = model.patch_len, model.input_channels
         N = (T + P - 1) // P
@@ -278,6 +283,7 @@ class Engine:
         self.workspaces = {}
 
     def weights(self, device):
+        device = self._resolve(device)
         if self.packed is None or self.packed.device != device:
             self.packed = PackedWeights(self.model, device)
         elif self.packed.dirty or self.packed.stale(self.model, device):
@@ -289,6 +295,7 @@ class Engine:
         return self.packed
 
     def workspace(self, B, T, Bt, device, keep_blocks=False):
+        device = self._resolve(device)
         key = (B, T, Bt, device, keep_blocks)
         ws = self.workspaces.get(key)
         if ws is None:
@@ -300,6 +307,14 @@ class Engine:
     @staticmethod
     def _dev_index(device):
         return device.index if device.index is not None else torch.cuda.current_device()
+
+    @staticmethod
+    def _resolve(device):
+        """torch.device('cuda') -> torch.device('cuda', current): cache keys compare indexed devices only."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device
 
     def modulation(self, ws, t):
         """t f32 [Bt] (device) -> ws.mod [Bt, depth*6D]."""
@@ -327,7 +342,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ training step
     def train_buffers(self, B, T, device):
-        key = (B, T, device)
+        key = (B, T, self._resolve(device))
         tb = getattr(self, "_train", {}).get(key)
         if tb is None:
             self._train = {key: TrainBuffers(self.model, B, T, device)}
@@ -346,8 +361,10 @@ class Engine:
         dev = x_t.device
         lib, ctx = L.load(), L.context(self._dev_index(dev))
         pw = self.weights(dev)
-        ws = self.workspace(B, T, B, dev)
         tb = self.train_buffers(B, T, dev)
+        ws = tb.ws
+        self._generation = getattr(self, "_generation", 0) + 1
+        tb.generation = self._generation   # the saved activations now belong to THIS forward (checked by every backward stage)
         tb.sv.dropout_p, tb.sv.seed = float(dropout_p), int(seed)
         out = torch.empty(B, Cc, T, dtype=torch.float32, device=dev)
         code = lib.jat_dit_forward_train(ctx, C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), x_t.data_ptr(),
@@ -358,30 +375,41 @@ class Engine:
         L.check(code)
         return out
 
-    def _bwd_args(self, dev, B, T):
-        pw, ws, tb = self.packed, self.workspace(B, T, B, dev), self.train_buffers(B, T, dev)  # the forward's copies, as they are
-        if pw is None or pw.device != dev:
+    @property
+    def generation(self):
+        """Id of the latest forward_train (0 = none yet); a backward stage passes the id of ITS forward."""
+        return getattr(self, "_generation", 0)
+
+    def _bwd_args(self, dev, B, T, generation=None):
+        pw = self.packed
+        tb = getattr(self, "_train", {}).get((B, T, self._resolve(dev)))
+        if pw is None or pw.device != self._resolve(dev) or tb is None or tb.generation == 0:
             raise L.JatError(L.ERR_BAD_ARG, "backward without a matching forward_train on this device")
+        if generation is not None and tb.generation != generation:
+            # single-slot training state: the activations this backward needs were overwritten by a later train-mode forward
+            raise L.JatError(L.ERR_BAD_ARG, "backward of a stale forward: another train-mode forward ran on this model before "
+                             "this backward (the saved activations are single-slot); run forward -> backward pairs in order, "
+                             "or wrap additional forwards in torch.no_grad() / model.eval()")
         pw.dirty = True
         gr = self.grads(dev)
-        return (L.context(self._dev_index(dev)), C.byref(pw.struct), C.byref(ws.struct), C.byref(tb.sv), C.byref(tb.sc),
+        return (L.context(self._dev_index(dev)), C.byref(pw.struct), C.byref(tb.ws.struct), C.byref(tb.sv), C.byref(tb.sc),
                 C.byref(gr.struct)), gr
 
-    def backward_begin(self, d_out, B, T):
+    def backward_begin(self, d_out, B, T, generation=None):
         """Stage 1 of the backward pass (final layer); zeroes the packed gradient buffers first."""
         dev = d_out.device
-        args, gr = self._bwd_args(dev, B, T)
+        args, gr = self._bwd_args(dev, B, T, generation)
         gr.zero_()
         L.check(L.load().jat_dit_backward_begin(*args, d_out.data_ptr(), B, T, torch.cuda.current_stream(dev).cuda_stream))
         return gr.by_param
 
-    def backward_block(self, i, B, T, dev):
-        args, gr = self._bwd_args(dev, B, T)
+    def backward_block(self, i, B, T, dev, generation=None):
+        args, gr = self._bwd_args(dev, B, T, generation)
         L.check(L.load().jat_dit_backward_block(*args, i, B, T, torch.cuda.current_stream(dev).cuda_stream))
         return gr.by_param
 
-    def backward_end(self, B, T, dev):
-        args, gr = self._bwd_args(dev, B, T)
+    def backward_end(self, B, T, dev, generation=None):
+        args, gr = self._bwd_args(dev, B, T, generation)
         L.check(L.load().jat_dit_backward_end(*args, B, T, torch.cuda.current_stream(dev).cuda_stream))
         return gr.by_param
 

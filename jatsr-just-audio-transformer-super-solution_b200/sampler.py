@@ -66,6 +66,10 @@ def flow_matching_sample(model, lr_latent, num_steps=50, cfg_scale=1.0, device="
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("jat_b200 sampler runs on CUDA only; there is no CPU fallback")
+    if device.index is None:
+        # the reference's default is device='cuda' (no index); torch.device('cuda') != torch.device('cuda:0'), so resolve
+        # it once: the plan key, the packed weights and the tensors all carry the same indexed device and the caches hit
+        device = torch.device("cuda", torch.cuda.current_device())
     if verbose:
         print(f"  Flow Matching sampling ({num_steps} steps, CFG scale={cfg_scale})...")
     if model.training:

@@ -5,7 +5,15 @@ def show_bench(path):
     k=d.pop('kernels',{})
     print(f"value {d['value']} {d['unit']}  ms/step {d['ms_per_step']}  step_tflops {d.get('step_tflops')} frac {d.get('step_tensor_frac_sustained')}  e2e {d.get('e2e',{}).get('value') if d.get('e2e') else None}  clocks {d.get('clocks')}")
     print("roofline", d.get('roofline')); print("cpu", d.get('cpu_baseline'))
-    for n,e in sorted(k.items(), key=lambda x:-x[1]['ms_per_step']): print(f"  {n:24s} {e['ms_per_step']:8.3f} ms  share {e['share']:.3f}  {e.get('achieved')} {e.get('unit')} frac {e.get('frac')}")
+    for n,e in sorted(k.items(), key=lambda x:-x[1]['ms_per_step']): print(f"  {n:24s} {e['ms_per_step']:8.3f} ms  share {e.get('share', e.get('share_of_kernel_time')):.3f}  {e.get('achieved')} {e.get('unit')} frac {e.get('frac')}")
+    print("kernel share of step", d.get('kernel_time_share_of_step'))
+    for sub in ('train','long','v2','gpu_baseline'):
+        r=d.get(sub)
+        if not r: continue
+        r=dict(r); kk=r.pop('kernels',None); r.pop('config',None)
+        print(sub.upper(), json.dumps(r)[:1500])
+        if kk:
+            for n,e in sorted(kk.items(), key=lambda x:-x[1]['ms_per_step']): print(f"    {n:24s} {e['ms_per_step']:8.3f} ms x{e['launches_per_step']}")
 def show_kernels(path):
     for l in open(path):
         try: d=json.loads(l)

@@ -71,3 +71,56 @@ def test_fullsize_per_block_and_50_step_parity(cls, rms):
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
         json.dump(report, open(os.path.join(out_dir, f"fullsize_parity_{cls}.json"), "w"), indent=1)
+
+
+C2 = dict(input_channels=1024, cond_channels=1024, patch_len=4, hidden_size=1024, depth=16, num_q_heads=16, num_kv_heads=4,
+          bottleneck_dim=512, mlp_ratio=4.0, dropout=0.1, drop_path_rate=0.0)   # train_ddp_v2.py:64-76 (288 M parameters)
+
+
+def test_c2_v2_full_depth_b1_25_step_sampler():
+    """BASELINE configs[1]: the v2 DiT (1024 / 16 blocks / 16Q / 4KV) at the reference's own inference batch
+    (B = 1 -> B_eff = 2, 690 token rows -- the small-M regime), full depth.  (1) one CFG forward, per block and at the
+    output, against the numpy oracle; (2) the 25-step CFG = 3.0 sampler against the fp32 torch restatement on the GPU, with
+    torch's bf16 autocast on the same computation as the yardstick (<= 1.5 x)."""
+    import numpy as np
+    import jat_b200
+    from oracle import dit_oracle as O   # checker only
+    from tests._torch_dit import flow_matching_sample
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(2)
+    model = rerandomise_zero_init(jat_b200.JaT_AudioSR_V2(**C2), seed=3, bf16_exact=False).eval()
+    assert 280e6 < sum(p.numel() for p in model.parameters()) < 300e6
+    w = {k: v.detach().float().numpy() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(12)
+    T = 1378
+    z, lr = torch.randn(1, 1024, T, generator=g), torch.randn(1, 1024, T, generator=g)
+    t = torch.full((2,), 0.4)
+    want, want_blocks = O.dit_forward(w, torch.cat([z, z]).numpy(), t.numpy(), torch.cat([lr, torch.zeros_like(lr)]).numpy(),
+                                      num_q_heads=16, num_kv_heads=4, return_blocks=True)
+    model = model.to(dev)
+    with torch.no_grad():
+        got, blocks = model.forward_with_blocks(torch.cat([z, z]).to(dev), t.to(dev), torch.cat([lr, torch.zeros_like(lr)]).to(dev))
+    N = want_blocks[0].shape[1]
+    errs = [rel_l2(blocks[i].view(2, N, -1).cpu(), torch.from_numpy(want_blocks[i])) for i in range(C2["depth"])]
+    assert max(errs) <= 0.012, errs                        # the per-block tolerance of tests/test_model_gpu.py
+    assert np.abs(want).max() > 0.05 and rel_l2(got.cpu(), torch.from_numpy(want)) <= 0.0135
+    prm = {k: v.detach() for k, v in model.state_dict().items()}
+    z0 = torch.randn(1, 1024, T, generator=g).to(dev)
+    lr = lr.to(dev)
+    with torch.no_grad():
+        want_z = flow_matching_sample(prm, C2, lr, z0, num_steps=25, cfg_scale=3.0)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ac_z = flow_matching_sample(prm, C2, lr, z0, num_steps=25, cfg_scale=3.0).float()
+    got_z = jat_b200.flow_matching_sample(model, lr, num_steps=25, cfg_scale=3.0, device="cuda", verbose=False, z0=z0)
+    ours, yard = rel_l2(got_z, want_z), rel_l2(ac_z, want_z)
+    print("C2_PARITY " + json.dumps({"per_block_max_rel_l2": max(errs), "final_latent_rel_l2_25_steps": ours,
+                                     "final_latent_autocast_rel_l2_25_steps": yard}))
+    assert torch.isfinite(got_z).all() and ours <= 1.5 * yard, (ours, yard)
+    # the sampler's plan / packed weights / captured graph are reused by a second call with the reference's default device='cuda'
+    plans = model.__dict__["_sampler_plans"]
+    plan = next(iter(plans.values()))
+    packed, graph = model._engine.packed, plan.graph
+    again = jat_b200.flow_matching_sample(model, lr, num_steps=25, cfg_scale=3.0, device="cuda", verbose=False, z0=z0)
+    assert torch.equal(again, got_z)
+    assert model._engine.packed is packed and next(iter(plans.values())) is plan and plan.graph is graph and graph is not None
