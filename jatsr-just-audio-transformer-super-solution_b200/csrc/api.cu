@@ -1108,16 +1108,27 @@ extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, cons
     p.scale = 0.125f;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     if (!make_drop(drop_p, drop_seed, &p.drop)) return fail(JAT_ERR_BAD_ARG, "jat_gqa_attention_bwd: drop_p must be in [0, 1)");
-    JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel, ATTB_SMEM_BYTES));
+    p.trace = ctx->att_trace;
+    // v2 (default): query-row threads, score MMAs overlapped with the math; JAT_ATTN_BWD=1 selects the first version
+    static const bool use_v1 = getenv("JAT_ATTN_BWD") && atoi(getenv("JAT_ATTN_BWD")) == 1;
     dim3 grid((N + ATTB_TILE - 1) / ATTB_TILE, Hkv, B);
     pre_launch(ctx, TAG_ATTN_BWD, s);
-    gqa_attention_bwd_kernel<<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+    if (use_v1) {
+        JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_v1_kernel, ATTB_SMEM_BYTES));
+        gqa_attention_bwd_v1_kernel<<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+    } else if (p.drop.thresh != 0u) {
+        JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel<true>, ATTB2_SMEM_BYTES));
+        gqa_attention_bwd_kernel<true><<<grid, ATTB_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+    } else {
+        JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel<false>, ATTB2_SMEM_BYTES));
+        gqa_attention_bwd_kernel<false><<<grid, ATTB_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+    }
     JAT_TRY(post_launch(ctx, "gqa_attention_bwd"));
     {
         const long long n = (long long)rows * Hq * 8;
         pre_launch(ctx, TAG_ATTN_BWD, s);
         attn_bwd_dq_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dq_acc_scratch, (__nv_bfloat16*)dqkv, rope_cos,
-                                                                              rope_sin, B, N, Hq, Hkv);
+                                                                              rope_sin, B, N, Hq, Hkv, use_v1 ? 1.0f : p.scale);
         return post_launch(ctx, "attn_bwd_dq_finalize");
     }
 }
