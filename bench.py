@@ -169,6 +169,11 @@ class Dist:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
+            # DDP training (configs[3]): NCCL's all-reduce kernels and the library's persistent GEMM grids must not fight for
+            # SMs -- a GEMM CTA that waits for an SM held by a long-running NCCL CTA delays its whole statically scheduled
+            # grid (weight-gradient GEMMs +15 %, GELU' dgrad +35 % measured).  NCCL is capped at 8 CTAs and the GEMM grids
+            # leave 8 SMs free (train_record: jat_set_gemm_sm_reserve); measured at 2 / 8 GPUs in DESIGN.md section 6.
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("JAT_NCCL_MAX_CTAS", "8"))
             if os.environ.get("JAT_NCCL_HIPRI", "1") == "1":
                 dist.init_process_group("nccl", init_method="env://",
                                         pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
@@ -338,13 +343,21 @@ def train_record(a, K, W, D_, model=None):
     model.train()
     model.grad_handoff = os.environ.get("JAT_GRAD_HANDOFF", "view")   # zero-copy .grad (the step calls zero_grad(set_to_none=True))
     net = model
+    # gradient exchange: f32 (the reference's) up to 2 GPUs, bf16 payload (jat_b200.ddp, two fused passes) from 4 GPUs on, where
+    # the ring moves 1.75-1.9 x the gradient bytes per rank and 8 NCCL CTAs cannot hide 3.06 GB of f32 behind the backward
+    grad_wire = os.environ.get("JAT_DDP_GRAD_DTYPE", "bf16" if world >= 4 else "f32")
+    sm_reserve = int(os.environ.get("JAT_SM_RESERVE", "8")) if world > 1 else 0
     if world > 1:
+        from jat_b200 import ops as _ops
+        _ops.set_gemm_sm_reserve(dev, sm_reserve)
         net = torch.nn.parallel.DistributedDataParallel(
             model, device_ids=[local], find_unused_parameters=False,
-            # the reference's call (train_ddp_v3mod2.py:822) + two DDP options measured at 2 GPUs: gradients as views of
-            # the all-reduce buckets (no copy back) and 200 MB buckets
-            bucket_cap_mb=int(os.environ.get("JAT_DDP_BUCKET_MB", "200")),
+            # the reference's call (train_ddp_v3mod2.py:822) + gradients as views of the all-reduce buckets (no copy back);
+            # torch's default 25 MB buckets: the all-reduce of the LAST bucket cannot overlap anything, so it should be small
+            bucket_cap_mb=int(os.environ.get("JAT_DDP_BUCKET_MB", "25")),
             gradient_as_bucket_view=os.environ.get("JAT_DDP_BUCKET_VIEW", "1") == "1")
+        if grad_wire == "bf16":   # bf16 payload through two fused library passes (jat_b200.ddp)
+            jat_b200.ddp.register_bf16_allreduce(net)
     fused_opt = os.environ.get("JAT_BENCH_TORCH_OPT", "0") == "0"
     if fused_opt:   # clip_grad_norm_(1.0) + AdamW + bf16 re-pack in two multi-tensor passes (jat_b200.FusedAdamW)
         opt = jat_b200.FusedAdamW(model.parameters(), lr=5e-5, weight_decay=0.1, max_grad_norm=1.0, model=model)
@@ -376,8 +389,10 @@ def train_record(a, K, W, D_, model=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         D_.barrier()
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(n):
             out = step()
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / n   # time the host needs to ISSUE a step (no sync inside)
         e1.record()
         D_.barrier()
         return D_.max(e0.elapsed_time(e1)), out
@@ -389,6 +404,7 @@ def train_record(a, K, W, D_, model=None):
     ctx, lib = L.context(local), L.load()
     l0 = lib.jat_launch_count(ctx)
     ms, loss = timed(K)
+    host_issue_ms = timed.host_ms
     clk = clocks.stop()
     launches = lib.jat_launch_count(ctx) - l0
     assert torch.isfinite(loss).all()
@@ -449,14 +465,18 @@ def train_record(a, K, W, D_, model=None):
                                   "MSE x-prediction loss, backward (grad_handoff=" + model.grad_handoff + "), clip_grad_norm_(1.0) + AdamW + bf16 weight re-pack "
                                   + ("(jat_b200.FusedAdamW: 2 multi-tensor passes)" if fused_opt else "(torch: foreach clip, fused AdamW, re-cast)"),
                       "norm": a.norm, "dropout": CFG["dropout"], "drop_path": CFG["drop_path_rate"], "cond_noise_ratio": 0.05,
-                      "parallelism": (f"DDP x{world} (torch DistributedDataParallel, f32 NCCL gradient all-reduce on a high-priority stream, "
-                                      "200 MB buckets, gradient_as_bucket_view)") if world > 1 else "single GPU"},
+                      "parallelism": (f"DDP x{world} (torch DistributedDataParallel, {grad_wire} NCCL gradient all-reduce on a high-priority stream, "
+                                      f"{os.environ.get('JAT_DDP_BUCKET_MB', '25')} MB buckets, gradient_as_bucket_view, NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}, "
+                                      f"{sm_reserve} SMs kept out of the GEMM grids)") if world > 1 else "single GPU"},
            "clocks": clk, "gpu_launches": int(launches), "loss": round(float(loss.item()), 5),
+           "host_issue_ms_per_step": round(host_issue_ms, 3),
            "step_tflops_per_gpu": round(step_flops / (ms / K) / 1e9, 1),
            "step_tensor_frac_sustained": round(step_flops / (ms / K) / 1e9 / pkz["tf"], 4),
            "rooflines": roofs, "kernels": kernels, "kernel_ms_per_step": round(tot / pk, 2),
            "params_identical_across_ranks": checksum_ok if world > 1 else None,
            "param_checksum": float(chk.item())}
+    if world > 1:
+        _ops.set_gemm_sm_reserve(dev, 0)
     if nosync_ms is not None:
         rec["no_sync_ms_per_step"] = round(nosync_ms, 3)
         rec["allreduce_exposed_ms"] = round(ms / K - nosync_ms, 3)
@@ -564,6 +584,12 @@ def v2_record(a, D_):
         torch.cuda.synchronize(dev)
         out[tag] = e0.elapsed_time(e1) / (reps * steps)
     assert torch.isfinite(z).all()
+    from jat_b200 import _lib as L
+    L.profile_begin(D_.local)   # per-class kernel time of one launch-by-launch run (CUDA event pair around every launch)
+    jat_b200.flow_matching_sample(model, lr, num_steps=steps, cfg_scale=CFG_SCALE, device=dev, verbose=False, use_graph=False)
+    prof = L.profile_end(D_.local)
+    kernels = {n: {"us_per_launch": round(v[0] / v[1] * 1e3, 2), "launches_per_step": round(v[1] / steps, 1),
+                   "ms_per_step": round(v[0] / steps, 4)} for n, v in prof.items()}
     N = (T + 3) // 4
     flops = 2 * N * model_flops_per_token(CFG_V2, N)
     best = min(out.values())
@@ -572,7 +598,8 @@ def v2_record(a, D_):
             "unit": "steps/s", "ms_per_step": round(best, 4), "ms_per_step_graph": round(out["graph"], 4),
             "ms_per_step_launch_by_launch": round(out["launches"], 4),
             "step_tflops": round(flops / best / 1e9, 1), "step_tensor_frac_sustained": round(flops / best / 1e9 / pk["tf"], 4),
-            "ideal_ms_per_step_at_sustained_peak": round(flops / pk["tf"] / 1e9, 4),
+            "ideal_ms_per_step_at_sustained_peak": round(flops / pk["tf"] / 1e9, 4), "kernels": kernels,
+            "kernel_sum_ms_per_step": round(sum(k["ms_per_step"] for k in kernels.values()), 4),
             "config": {"workload": "configs[1]: v2 DiT 1024/16/16Q/4KV, CFG=3.0, 25 Euler steps, batch 1 x [1024,1378] "
                                    "(B_eff 2, 690 token rows)", "norm": a.norm}}
 

@@ -443,6 +443,13 @@ int jat_gate_bwd_dropout(jat_ctx* ctx, const float* dx, const void* y_bf16, cons
 int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, int M, int cols, float* out, void* stream);
 int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, void* stream);
 
+/* Gradient exchange in bf16 (replaces the f32 payload of DDP's bucketed all-reduce, reference train_ddp_v3mod2.py:822, 922):
+ *   jat_grad_compress:   out_bf16[i] = bf16(in[i] * scale)   -- scale = 1 / world size, so that a SUM all-reduce yields the mean
+ *   jat_grad_decompress: out[i] = float(in_bf16[i])           -- back into the f32 gradient bucket
+ * Both buffers 16-byte aligned, n elements; one pass each (6 bytes per element).  Used by jat_b200.ddp.bf16_allreduce_hook. */
+int jat_grad_compress(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, float scale, void* stream);
+int jat_grad_decompress(jat_ctx* ctx, const void* in_bf16, float* out, int64_t n, void* stream);
+
 /* ----------------------------------------------------------------------------------------------
  * The elementwise work either side of the model call in the training step (train_ddp_v3mod2.py:856-889,
  * train_ddp_v3m2.py:547-585), one pass each instead of ~10 torch kernels and 8 `.item()` syncs.

@@ -146,6 +146,8 @@ SIGNATURES = {
     "jat_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "jat_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "jat_cast_f32_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "jat_grad_compress": (_i, [_vp, _vp, _vp, _i64, C.c_float, _vp]),
+    "jat_grad_decompress": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "jat_train_inputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "jat_mse_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "jat_chunk_normalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -472,9 +472,33 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     const bool a_mn = e->a_transposed != 0, w_mn = e->w_transposed != 0;
     if ((K % 64 != 0 && !(a_mn && w_mn)) || N % 128 != 0)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
+    const bool auto_cfg = cta_pair < 0 && block_n == 0 && ctx->gemm_block_n == 0 && ctx->gemm_cta_pair == 1 && !(a_mn && w_mn);
     if (cta_pair < 0) cta_pair = ctx->gemm_cta_pair;
     if (block_n == 0) block_n = ctx->gemm_block_n;
     if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
+    if (auto_cfg && block_n == 256) {
+        // Small-M regime (B = 1 inference: M = 345-690 token rows, BASELINE configs[1]): the default 256 x 256 CTA-pair tiles
+        // leave most of the machine idle (out_proj / fc2 of the v2 model: 12 tiles on 74 pairs) and the launch lasts as long
+        // as ONE tile's K loop.  Makespan model per candidate: rounds of the persistent schedule x (k-blocks x MMA time of a
+        // k-block + epilogue); small tiles pay ~15 % (128-wide: operand stream per FLOP doubles) / ~10 % (single CTA: no
+        // W-tile sharing).  The default is kept unless a candidate is at least 20 % cheaper -- large problems never switch.
+        const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+        const int ks = e->k_splits > 1 ? e->k_splits : 1;
+        auto cost = [&](int cg_, int bn_) -> double {
+            const long long items = (long long)((M + 128 * cg_ - 1) / (128 * cg_)) * (N / bn_) * ks;
+            const long long workers = ctx->gemm_sms / cg_;
+            const long long rounds = (items + workers - 1) / workers;
+            const double kb_clk = 2.0 * bn_ * (bn_ == 128 ? 1.15 : 1.0) * (cg_ == 1 ? 1.10 : 1.0);
+            return (double)rounds * ((double)((kblocks + ks - 1) / ks) * kb_clk + 8.0 * bn_);
+        };
+        const double base = cost(2, 256);
+        double best = base * 0.8;
+        const int cand[3][2] = {{2, 128}, {1, 256}, {1, 128}};
+        for (int i = 0; i < 3; ++i) {
+            const double c = cost(cand[i][0], cand[i][1]);
+            if (c < best) { best = c; cta_pair = cand[i][0] == 2 ? 1 : 0; block_n = cand[i][1]; }
+        }
+    }
     if (block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: block_n must be 128 or 256");
     if (N % block_n != 0) block_n = 128;
     const int cg = cta_pair ? 2 : 1;
@@ -854,6 +878,32 @@ extern "C" int jat_cast_f32_bf16(jat_ctx* ctx, const float* in, void* out_bf16, 
     return post_launch(ctx, "cast_f32_bf16");
 }
 
+// Gradient buckets <-> bf16 all-reduce payload (jat_b200.ddp.bf16_allreduce_hook)
+extern "C" int jat_grad_compress(jat_ctx* ctx, const float* in, void* out_bf16, int64_t n, float scale, void* stream) {
+    DeviceGuard dev_guard__(ctx);
+    if (!ctx || !in || !out_bf16 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_grad_compress: bad argument");
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) != 0)
+        return fail(JAT_ERR_BAD_ARG, "jat_grad_compress: buffers must be 16-byte aligned");
+    long long blocks = (n / 8 + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 8;
+    blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    grad_compress_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, (long long)n, scale);
+    return post_launch(ctx, "grad_compress");
+}
+extern "C" int jat_grad_decompress(jat_ctx* ctx, const void* in_bf16, float* out, int64_t n, void* stream) {
+    DeviceGuard dev_guard__(ctx);
+    if (!ctx || !in_bf16 || !out || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_grad_decompress: bad argument");
+    if (((reinterpret_cast<uintptr_t>(in_bf16) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+        return fail(JAT_ERR_BAD_ARG, "jat_grad_decompress: buffers must be 16-byte aligned");
+    long long blocks = (n / 8 + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 8;
+    blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+    pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
+    grad_decompress_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_bf16, out, (long long)n);
+    return post_launch(ctx, "grad_decompress");
+}
+
 // ------------------------------------------------------------------------------------------------ training-step glue
 extern "C" int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, const float* hr_mean, const float* hr_std,
                                 const float* lr_mean, const float* lr_std, const float* noise, const float* cond_noise,
@@ -1013,7 +1063,19 @@ static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, 
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
-    dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv, B);
+    // query heads per CTA: the whole KV group (K / V staged once for its G heads) unless that leaves SMs without a CTA
+    // (B = 1 inference): then the group is split over several CTAs, each staging K / V itself
+    int gs = p.G;
+    {
+        const long long ctas = (long long)((N + ATT_BQ - 1) / ATT_BQ) * Hkv * B;
+        for (int d = p.G; d >= 1; --d) {
+            if (p.G % d != 0) continue;
+            gs = d;
+            if (ctas * (p.G / d) >= ctx->sm_count) break;
+        }
+    }
+    p.Gs = gs;
+    dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv * (p.G / gs), B);
     // key range padded to NK = 2*NKH columns (two softmax warpgroups); padded keys are masked in-kernel
     if (p.drop.thresh != 0u) {
         if (nkeys <= 64) return launch_attention<32, true>(ctx, tq, qkv, rows, cols, p, grid, s);
@@ -1112,16 +1174,17 @@ extern "C" int jat_gqa_attention_bwd_dropout(jat_ctx* ctx, const void* qkv, cons
     // v2 (default): query-row threads, score MMAs overlapped with the math; JAT_ATTN_BWD=1 selects the first version
     static const bool use_v1 = getenv("JAT_ATTN_BWD") && atoi(getenv("JAT_ATTN_BWD")) == 1;
     dim3 grid((N + ATTB_TILE - 1) / ATTB_TILE, Hkv, B);
+    const dim3 grid1d((unsigned)(grid.x * grid.y * grid.z));   // v2 decodes (key tile, KV head, batch item) itself, heavy tiles first
     pre_launch(ctx, TAG_ATTN_BWD, s);
     if (use_v1) {
         JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_v1_kernel, ATTB_SMEM_BYTES));
         gqa_attention_bwd_v1_kernel<<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
     } else if (p.drop.thresh != 0u) {
         JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel<true>, ATTB2_SMEM_BYTES));
-        gqa_attention_bwd_kernel<true><<<grid, ATTB_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+        gqa_attention_bwd_kernel<true><<<grid1d, ATTB2_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
     } else {
         JAT_TRY(ensure_dyn_smem(ctx, (const void*)gqa_attention_bwd_kernel<false>, ATTB2_SMEM_BYTES));
-        gqa_attention_bwd_kernel<false><<<grid, ATTB_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
+        gqa_attention_bwd_kernel<false><<<grid1d, ATTB2_THREADS, ATTB2_SMEM_BYTES, s>>>(tqkv, tdo, tdq, p);
     }
     JAT_TRY(post_launch(ctx, "gqa_attention_bwd"));
     {

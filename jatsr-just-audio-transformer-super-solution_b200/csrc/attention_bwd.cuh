@@ -45,7 +45,7 @@ struct AttnBwdParams {
 };
 #define ATTB_TRACE(slot)                                                                                   \
     do {                                                                                                   \
-        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[(slot)] = clock64(); \
+        if (p.trace && blockIdx.x == 0) p.trace[(slot)] = clock64(); \
     } while (0)
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
@@ -404,6 +404,7 @@ __device__ __forceinline__ void attb_chunk_math(uint32_t (&sv)[32], const uint32
     }
 }
 
+constexpr int ATTB2_THREADS = 512;  // 4 service warps + 8 compute warps + 4 dQ read-out warps
 constexpr int ATTB2_SMEM_BYTES = 2 * ATTB_TILE_BYTES      // K, V
                                  + 4 * ATTB_TILE_BYTES    // Q, dO double-buffered
                                  + 4 * ATTB_TILE_BYTES    // P, dS ([128 queries x 128 keys] bf16 = 2 key blocks each)
@@ -411,7 +412,7 @@ constexpr int ATTB2_SMEM_BYTES = 2 * ATTB_TILE_BYTES      // K, V
                                  + 256 + 1024;
 
 template <bool DROP>
-__global__ void __launch_bounds__(ATTB_THREADS, 1)
+__global__ void __launch_bounds__(ATTB2_THREADS, 1)
 gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -432,11 +433,22 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     uint64_t* bar_sp_free = bars + 6;   // S, dP copied to registers by the 256 compute threads
     uint64_t* bar_pds_full = bars + 7;  // P, dS written (256 compute threads)
     uint64_t* bar_mma2_done = bars + 8; // dV, dK, dQ MMAs retired: P / dS tiles free, dQ complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_dq_free = bars + 9;   // [2] dQ buffer copied to registers by the 128 read-out threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int kt = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    // 1-D grid, heaviest work first: every full 128-key tile of every (KV head, batch item) precedes the partial last key
+    // tiles (N = 345: 89 of 128 keys, ~70 % of the work), so the short CTAs fill the last, partial wave of the launch
     const int QT = (p.N + ATTB_TILE - 1) / ATTB_TILE;
+    int kt, g, b;
+    {
+        const int kt_full = p.N / ATTB_TILE, per = p.Hkv * p.B, lin = (int)blockIdx.x;
+        int rest;
+        if (lin < kt_full * per) { kt = lin % kt_full; rest = lin / kt_full; }
+        else { const int l2 = lin - kt_full * per, kp = QT - kt_full; kt = kt_full + l2 % kp; rest = l2 / kp; }
+        g = rest % p.Hkv;
+        b = rest / p.Hkv;
+    }
     const int iters = p.G * QT;
     const int row_b = b * p.N;  // first token row of this batch item
 
@@ -447,6 +459,8 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         mbar_init(bar_sp_free, 256);
         mbar_init(bar_pds_full, 256);
         mbar_init(bar_mma2_done, 1);
+        mbar_init(&bar_dq_free[0], 128);
+        mbar_init(&bar_dq_free[1], 128);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -461,7 +475,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
 
     if (warp < 4) {
     // service warpgroup (TMA producer, MMA issuer, two idle warps): hands registers to the compute warpgroups
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -520,6 +534,7 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                 if (lane == 0 && it < 16) ATTB_TRACE(128 + it * 4 + 1);
             }
             mbar_wait(bar_pds_full, (uint32_t)(it & 1));
+            if (it >= 2) mbar_wait(&bar_dq_free[st], (uint32_t)(((it - 2) >> 1) & 1));  // dQ buffer `st` was read out (iteration it - 2)
             tc_fence_after();
             if (lane == 0 && it < 16) ATTB_TRACE(128 + it * 4 + 2);
             const uint64_t q_desc_mn = umma_smem_desc_sw128_mn(smem_u32(sQ + st * ATTB_TILE_BYTES), ATTB_TILE_BYTES);
@@ -548,9 +563,9 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         }
         __syncwarp();
     }
-    } else {
+    } else if (warp < 12) {
         // ------------------------------------------------------------------ compute warps: thread = QUERY row
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         // Two warps per TMEM lane quadrant: group 0 (warps 4-7) takes keys [0, 64) of the tile, group 1 (warps 8-11) keys [64, 128).
         const int grp = (warp - 4) >> 2;
         const int r = (warp & 3) * 32 + lane;
@@ -560,43 +575,24 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t sP_row = smem_u32(sP) + (uint32_t)grp * ATTB_TILE_BYTES + row_off;
         const uint32_t sdS_row = smem_u32(sdS) + (uint32_t)grp * ATTB_TILE_BYTES + row_off;
-        const uint32_t sdQ_row = smem_u32(sdQ) + row_off;
         const int key0 = kt * ATTB_TILE + grp * 64;   // first key of this thread's 64 columns
         const int nvalid = p.N - key0;                 // columns [0, nvalid) hold real keys (may be <= 0 or >= 64)
         const float sl2 = p.scale_log2e;
 
-        auto dq_epilogue = [&](int it) {  // dQ tile of iteration `it`: TMEM -> f32 smem boxes -> TMA reduce-add
-            const int h = g * p.G + it / QT, qt = it % QT;
-            if (t == 0) tma_store_wait_read<0>();  // the previous reduce-add has drained the staging tile
-            named_bar(1, 256);
-            {
-                const int bx = grp;  // each group moves one 32-column box of the [128 x 64] dQ tile
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + COL_DQ + (uint32_t)((it & 1) * 64 + bx * 32), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t addr = sdQ_row + (uint32_t)bx * ATTB_TILE_BYTES + ((((uint32_t)c) ^ rx) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
-                                 "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            named_bar(1, 256);
-            if (t == 0) {
-                tma_reduce_add_2d(&tmap_dq, sdQ, h * ATT_HD, row_b + qt * ATTB_TILE);
-                tma_reduce_add_2d(&tmap_dq, sdQ + ATTB_TILE_BYTES, h * ATT_HD + 32, row_b + qt * ATTB_TILE);
-                tma_store_commit();
-            }
-        };
         // per-query statistics of iteration `it` (queries past the batch item's N tokens: lse = +inf -> P = 0, dS = 0)
         auto load_stats = [&](int it, float& nl, float& dsum) {
             const int h = g * p.G + it / QT, q = (it % QT) * ATTB_TILE + r;
             const bool q_ok = q < p.N;
             const long long idx = ((long long)b * p.Hq + h) * p.N + (q_ok ? q : 0);
-            nl = q_ok ? -__ldg(p.lse + idx) : -INFINITY;
-            dsum = q_ok ? __ldg(p.dsum + idx) : 0.0f;
+            // (volatile: issued HERE, a whole math phase before the values are used -- the compiler otherwise sinks the loads
+            //  to their use and the warp waits out the full global-memory latency)
+            float l = INFINITY, d = 0.0f;
+            if (q_ok) {
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l) : "l"(p.lse + idx));
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(d) : "l"(p.dsum + idx));
+            }
+            nl = -l;
+            dsum = d;
         };
         float nl, dsum;
         load_stats(0, nl, dsum);
@@ -627,6 +623,20 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
             tmem_ld_32x32(t_dp + 32u, d1);
             attb_chunk_math<DROP>(s0, d0, &pp[0], &dd[0], sl2, my_nl, my_d, warp_live ? nvalid : 0, p.drop, rq, (uint32_t)key0);
             if (tr) ATTB_TRACE(it * 8 + 2);
+            // ---- the P / dS tiles are free once the dV / dK / dQ MMAs of the previous iteration have retired (they ran under
+            //      the math above); chunk 0 goes to shared memory now, its stores overlap the math of chunk 1
+            if (it > 0) {
+                mbar_wait(bar_mma2_done, (uint32_t)((it - 1) & 1));
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = (((uint32_t)i) ^ rx) << 4;
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sP_row + off), "r"(pp[4 * i]), "r"(pp[4 * i + 1]),
+                             "r"(pp[4 * i + 2]), "r"(pp[4 * i + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sdS_row + off), "r"(dd[4 * i]), "r"(dd[4 * i + 1]),
+                             "r"(dd[4 * i + 2]), "r"(dd[4 * i + 3]) : "memory");
+            }
             tmem_ld_wait_dep32(s1);
             tmem_ld_wait_dep32(d1);
             tc_fence_before();
@@ -636,13 +646,9 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                                   (uint32_t)(key0 + 32));
             // ---- the P / dS tiles are free once the dV / dK / dQ MMAs of the previous iteration have retired
             if (tr) ATTB_TRACE(it * 8 + 3);
-            if (it > 0) {
-                mbar_wait(bar_mma2_done, (uint32_t)((it - 1) & 1));
-                tc_fence_after();
-            }
             if (tr) ATTB_TRACE(it * 8 + 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {  // 64 keys = 128 bytes = 8 x 16 B chunks of this thread's row in key block `grp`
+            for (int i = 4; i < 8; ++i) {  // 64 keys = 128 bytes = 8 x 16 B chunks of this thread's row in key block `grp`
                 const uint32_t off = (((uint32_t)i) ^ rx) << 4;
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sP_row + off), "r"(pp[4 * i]), "r"(pp[4 * i + 1]),
                              "r"(pp[4 * i + 2]), "r"(pp[4 * i + 3]) : "memory");
@@ -660,12 +666,10 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                 tmem_ld_32x32(t_dp, d0);
             }
             if (tr) ATTB_TRACE(it * 8 + 6);
-            if (it > 0) dq_epilogue(it - 1);  // under the MMAs just released (they write the other dQ buffer)
             if (tr) ATTB_TRACE(it * 8 + 7);
         }
         mbar_wait(bar_mma2_done, (uint32_t)((iters - 1) & 1));
         tc_fence_after();
-        dq_epilogue(iters - 1);
         // ---- dV, dK of key row r (TMEM lane = key): dK through the transpose of the RoPE rotation (jat_audiosr_v2.py:70-91)
         {   // (tcgen05.ld is warp-collective: every lane loads, only rows that hold a real key store)
             const int key = kt * ATTB_TILE + r;
@@ -698,11 +702,16 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                     __nv_bfloat16* ok = orow + (p.Hq + g) * ATT_HD;
                     float ra[32], rb[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {  // forward: lo' = a c - b s, hi' = b c + a s  ->  da = glo c + ghi s, db = ghi c - glo s
-                        const float c = __ldg(cosr + j) * p.scale, s = __ldg(sinr + j) * p.scale;   // (1/sqrt(d) of dS, see above)
-                        const float glo = __uint_as_float(lo[j]), ghi = __uint_as_float(hi[j]);
-                        ra[j] = glo * c + ghi * s;
-                        rb[j] = ghi * c - glo * s;
+                    for (int j = 0; j < 32; j += 4) {  // forward: lo' = a c - b s, hi' = b c + a s  ->  da = glo c + ghi s, db = ghi c - glo s
+                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cosr + j)), s4 = __ldg(reinterpret_cast<const float4*>(sinr + j));
+                        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float c = cc[q] * p.scale, s = ss[q] * p.scale;   // (1/sqrt(d) of dS, see above)
+                            const float glo = __uint_as_float(lo[j + q]), ghi = __uint_as_float(hi[j + q]);
+                            ra[j + q] = glo * c + ghi * s;
+                            rb[j + q] = ghi * c - glo * s;
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
@@ -712,6 +721,46 @@ gqa_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
                                                                             pack_bf16(rb[j + 4], rb[j + 5]), pack_bf16(rb[j + 6], rb[j + 7]));
                     }
                 }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ dQ read-out warpgroup (warps 12-15 = TMEM lane quadrants 0-3)
+        // dQ tile of every iteration: TMEM -> registers (buffer handed back at once) -> f32 smem boxes -> TMA reduce-add into the
+        // f32 dQ accumulator.  Off the compute warps' critical path: their math never waits for this read-out.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        const int r = (warp & 3) * 32 + lane;
+        const int t = threadIdx.x - 384;  // 0..127 == r
+        const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t rx = (uint32_t)(r & 7);
+        const uint32_t sdQ_row = smem_u32(sdQ) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            const int h = g * p.G + it / QT, qt = it % QT;
+            mbar_wait_backoff(bar_mma2_done, (uint32_t)(it & 1));
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(t_row + COL_DQ + (uint32_t)((it & 1) * 64), v0);
+            tmem_ld_32x32(t_row + COL_DQ + (uint32_t)((it & 1) * 64 + 32), v1);
+            tmem_ld_wait_dep32(v0);
+            tmem_ld_wait_dep32(v1);
+            tc_fence_before();
+            mbar_arrive(&bar_dq_free[it & 1]);
+            if (t == 0) tma_store_wait_read<0>();  // the previous reduce-add has drained the staging tile
+            named_bar(1, 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t addr = sdQ_row + ((((uint32_t)c) ^ rx) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v0[4 * c]), "r"(v0[4 * c + 1]),
+                             "r"(v0[4 * c + 2]), "r"(v0[4 * c + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + (uint32_t)ATTB_TILE_BYTES), "r"(v1[4 * c]), "r"(v1[4 * c + 1]),
+                             "r"(v1[4 * c + 2]), "r"(v1[4 * c + 3]) : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar(1, 128);
+            if (t == 0) {
+                tma_reduce_add_2d(&tmap_dq, sdQ, h * ATT_HD, row_b + qt * ATTB_TILE);
+                tma_reduce_add_2d(&tmap_dq, sdQ + ATTB_TILE_BYTES, h * ATT_HD + 32, row_b + qt * ATTB_TILE);
+                tma_store_commit();
             }
         }
         if (t == 0) tma_store_wait_all<0>();

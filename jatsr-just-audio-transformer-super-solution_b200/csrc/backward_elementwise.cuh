@@ -403,6 +403,37 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
     }
 }
 
+// Gradient exchange in bf16 (DDP bucket -> NCCL payload and back; jat_b200.ddp): grid-stride, 128-bit accesses.
+//   compress:    out_bf16[i] = bf16(in_f32[i] * scale)      (scale = 1 / world size: the all-reduce then yields the mean)
+//   decompress:  out_f32[i]  = float(in_bf16[i])
+// One read of 4 B + one write of 2 B per element (resp. 2 + 4): HBM-bound, 6 B per element.
+__global__ void __launch_bounds__(256)
+grad_compress_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nvec = n >> 3;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * v), b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * v + 1);
+        reinterpret_cast<uint4*>(out)[v] = make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale),
+                                                      pack_bf16(b.x * scale, b.y * scale), pack_bf16(b.z * scale, b.w * scale));
+    }
+    for (long long j = (nvec << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        out[j] = __float2bfloat16(in[j] * scale);
+}
+__global__ void __launch_bounds__(256)
+grad_decompress_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nvec = n >> 3;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 w = __ldcs(reinterpret_cast<const uint4*>(in) + v);
+        reinterpret_cast<float4*>(out)[2 * v] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u),
+                                                            __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+        reinterpret_cast<float4*>(out)[2 * v + 1] = make_float4(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xffff0000u),
+                                                                __uint_as_float(w.w << 16), __uint_as_float(w.w & 0xffff0000u));
+    }
+    for (long long j = (nvec << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        out[j] = __bfloat162float(in[j]);
+}
+
 // out (bf16) = g (f32) * act'(u)   (tiny: the activation backward of the timestep path)
 template <int ACT>
 __global__ void dact_mul_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out,

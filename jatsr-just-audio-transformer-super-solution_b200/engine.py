@@ -125,7 +125,13 @@ class PackedWeights:
 
     @staticmethod
     def _versions(model):
-        return tuple((id(p), p._version, p.device) for p in model.parameters())
+        # (the module-tree walk of model.parameters() costs more than the 400 version reads: the list is cached on the model
+        #  and dropped by _apply / load_state_dict(assign=True)-style re-registration through the id check below)
+        plist = model.__dict__.get("_param_list")
+        if plist is None or len(plist) != model.__dict__.get("_param_count", -1):
+            plist = list(model.parameters())
+            model.__dict__["_param_list"], model.__dict__["_param_count"] = plist, len(plist)
+        return tuple((id(p), p._version, p.device) for p in plist)
 
     def stale(self, model, device):
         return device != self.device or self._versions(model) != self.versions

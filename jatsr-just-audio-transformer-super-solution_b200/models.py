@@ -192,7 +192,16 @@ class _JaTBase(nn.Module):
             nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
         self.final_layer = nn.Sequential(fin_norm, nn.Linear(hidden_size, patch_len * input_channels))
         self.initialize_weights()
+        # DistributedDataParallel (train_ddp_v3mod2.py:822, default broadcast_buffers=True) re-broadcasts every module buffer
+        # from rank 0 at the start of EVERY forward: here that is 84 RoPE tables (58 MB: cat + NCCL broadcast + copy back,
+        # measured 2.5 ms of a 53 ms step with the compute stream idle).  The tables are pure functions of (head_dim, base),
+        # identical on every rank by construction, so they are put on DDP's ignore list (the attribute DDP itself reads);
+        # both spellings, because DDP sees `_orig_mod.`-prefixed names when the module went through torch.compile first.
+        rope = [f"blocks.{i}.attn.rope.{n}" for i in range(depth) for n in ("inv_freq", "cos_cached", "sin_cached")]
+        self._ddp_params_and_buffers_to_ignore = rope + ["_orig_mod." + n for n in rope]
         object.__setattr__(self, "_engine", Engine(self))  # not a submodule / not in state_dict
+        # the engine caches the parameter list (see PackedWeights._versions); load_state_dict(assign=True) replaces parameters
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.__dict__.pop("_param_list", None))
         # How parameter gradients leave the backward pass.  "copy" (default): fresh tensors, ordinary autograd semantics
         # (accumulation over several backward passes, zero_grad(set_to_none=False), .grad kept across steps).  "view": the
         # .grad tensors are views of the library's packed gradient buffers (no 3 GB copy per step); they are valid until the
@@ -259,6 +268,7 @@ class _JaTBase(nn.Module):
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
+        self.__dict__.pop("_param_list", None)
         if getattr(self, "_engine", None) is not None:
             self._engine.packed = None  # .to()/.half()/... invalidates packed device copies
         return r

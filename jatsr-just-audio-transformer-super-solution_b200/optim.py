@@ -42,6 +42,9 @@ class _Group:
         self.dtype_bits = torch.tensor([1 if (d is not None and d.dtype == torch.bfloat16) else 0 for d in dsts],
                                        dtype=torch.int64)
         self.key = self._key(states)
+        # every tensor at the same step count (the usual case): kept as one python int, see upload()
+        st = [float(states[p]["step"]) for p in params]
+        self.uniform_step = int(st[0]) if all(x == st[0] for x in st) else None
         # two pinned staging buffers used alternately, each guarded by an event: the host may run a step ahead of the stream
         self.host = [torch.empty(n, 8, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.done = [None, None]
@@ -52,7 +55,10 @@ class _Group:
 
     def upload(self, steps, beta1, beta2):
         """Gradient pointers change from step to step (autograd hands out fresh tensors): column 1 + the vec_ok flag; the
-        bias corrections follow each tensor's own step count (torch/optim/adam.py keeps `step` per parameter)."""
+        bias corrections follow each tensor's own step count (torch/optim/adam.py keeps `step` per parameter).  Host cost
+        matters here: under DDP the host is NOT ahead of the GPU at the end of the backward, so every 100 us spent before the
+        update kernels are launched is a stall of the device.  The common case (every tensor at the same step) therefore
+        avoids the per-tensor work: one python-side step count, two scalars broadcast into the table."""
         g = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
         k = self.turn
         self.turn ^= 1
@@ -62,9 +68,15 @@ class _Group:
         h.copy_(self.static)
         h[:, 1] = g
         h[:, 6] = self.dtype_bits | ((self.static_ok & (g % 16 == 0)).to(torch.int64) << 32)
-        st = torch.stack(steps).to(torch.float64)
-        bc = torch.stack([1.0 - beta1 ** st, torch.sqrt(1.0 - beta2 ** st)], 1).to(torch.float32).contiguous()
-        h[:, 7] = bc.view(torch.int64).reshape(-1)      # two packed f32: bias_corr1 | bias_corr2_sqrt
+        if self.uniform_step is not None:
+            self.uniform_step += 1
+            st = float(self.uniform_step)
+            bc = torch.tensor([1.0 - beta1 ** st, (1.0 - beta2 ** st) ** 0.5], dtype=torch.float64).to(torch.float32)
+            h[:, 7] = bc.view(torch.int64)  # two packed f32: bias_corr1 | bias_corr2_sqrt, the same for every tensor
+        else:
+            st = torch.stack(steps).to(torch.float64)
+            bc = torch.stack([1.0 - beta1 ** st, torch.sqrt(1.0 - beta2 ** st)], 1).to(torch.float32).contiguous()
+            h[:, 7] = bc.view(torch.int64).reshape(-1)
         self.table.copy_(h, non_blocking=True)
         self.done[k] = torch.cuda.Event()
         self.done[k].record(torch.cuda.current_stream(self.table.device))

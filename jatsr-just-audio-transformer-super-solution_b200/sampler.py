@@ -23,6 +23,9 @@ from . import ops
 from .models import _JaTBase
 
 
+_MAX_PLANS = 4
+
+
 class _Plan:
     """Buffers (+ optional captured graph) for one (model, B, C, T, steps, cfg) sampling problem."""
 
@@ -79,13 +82,22 @@ def flow_matching_sample(model, lr_latent, num_steps=50, cfg_scale=1.0, device="
     if use_graph is None:
         use_graph = os.environ.get("JAT_B200_GRAPH", "1") != "0"
 
+    # Plans (buffers + captured graph) are kept per problem shape, a few at a time: the chunk loop of a long track alternates
+    # between the full-chunk batch and the short last chunk, and re-capturing 10 k launches (plus freeing the previous graph's
+    # memory) on every call cost more than the launches themselves.  A new PackedWeights object (weights re-allocated, e.g.
+    # after `.to()`) invalidates every captured graph; an in-place refresh keeps the pointers and the plans.
     cache = model.__dict__.setdefault("_sampler_plans", {})
     key = (B, Cc, T, num_steps, float(cfg_scale), device)
-    plan = cache.get(key)
-    if plan is None or model._engine.weights(device) is not plan.__dict__.get("packed"):
+    packed = model._engine.weights(device)
+    if any(pl.packed is not packed for pl in cache.values()):
         cache.clear()
-        plan = cache[key] = _Plan(model, B, Cc, T, num_steps, cfg_scale, device)
-        plan.packed = model._engine.weights(device)
+    plan = cache.pop(key, None)
+    if plan is None:
+        while len(cache) >= _MAX_PLANS:
+            cache.pop(next(iter(cache)))          # least recently used
+        plan = _Plan(model, B, Cc, T, num_steps, cfg_scale, device)
+        plan.packed = packed
+    cache[key] = plan                             # most recently used last
     plan.z.copy_(z_init)
     plan.lr.copy_(lr_latent.to(device=device, dtype=torch.float32))
 

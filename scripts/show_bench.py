@@ -13,7 +13,7 @@ def show_bench(path):
         r=dict(r); kk=r.pop('kernels',None); r.pop('config',None)
         print(sub.upper(), json.dumps(r)[:1500])
         if kk:
-            for n,e in sorted(kk.items(), key=lambda x:-x[1]['ms_per_step']): print(f"    {n:24s} {e['ms_per_step']:8.3f} ms x{e['launches_per_step']}")
+            for n,e in sorted(kk.items(), key=lambda x:-x[1]['ms_per_step']): print(f"    {n:24s} {e['ms_per_step']:8.3f} ms x{e['launches_per_step']}  {e.get('us_per_launch','')}")
 def show_kernels(path):
     for l in open(path):
         try: d=json.loads(l)
