@@ -74,6 +74,10 @@ int jat_adaln_norm_modulate(jat_ctx* ctx, const float* x, void* out_bf16, const 
  * P must be 4. */
 int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
                       void* out_bf16, int B, int C, int T, int P, void* stream);
+/* The same with a condition latent of its own channel count (reference ctor `cond_channels` != `input_channels`):
+ * x_t [xt_batch, C, T], x_cond [cond_batch, Cc, T] -> out bf16 [B*N, (C + Cc) * P]; C and Cc multiples of 32. */
+int jat_patchify_cast2(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch, void* out_bf16, int B, int C,
+                       int Cc, int T, int P, void* stream);
 
 /* Sinusoidal timestep features (TimeEmbedding.forward, jat_audiosr_v2.py:177-190), bf16 output
  * (the A operand of t_embedder.1):  out[b, i] = sin(t[b] * f_i), out[b, half + i] = cos(t[b] * f_i),
@@ -211,8 +215,8 @@ typedef struct jat_dit_weights {
     int32_t hidden, depth, n_q_heads, n_kv_heads, head_dim, mlp_hidden, bottleneck, channels, patch_len,
         norm_kind, max_len, rope_max_pos;
     float norm_eps;
-    int32_t reserved;
-    const void* pe_w1;   /* bf16 [bottleneck, 2*C*P]   patch_embed.proj.0.weight */
+    int32_t cond_channels; /* channels of x_cond (reference ctor `cond_channels`); 0 = the same as `channels` */
+    const void* pe_w1;   /* bf16 [bottleneck, (C+Cc)*P]   patch_embed.proj.0.weight */
     const float* pe_b1;  /* f32  [bottleneck] */
     const void* pe_w2;   /* bf16 [hidden, bottleneck]  patch_embed.proj.2.weight */
     const float* pe_b2;  /* f32  [hidden] */
@@ -470,6 +474,11 @@ int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, const float
                      const float* cond_scale_dev, float cond_scale, const float* keep, const float* t, float* hr_norm,
                      float* lr_cond, float* z_t, int B, int C, int T, void* stream);
 int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n, void* stream);
+/* Charbonnier reconstruction loss of the MOD3 training script (train_ddp_v3mod3.py:57-85): mean(sqrt((pred - target)^2 + eps)).
+ * stats5 (DEVICE double[5], overwritten) = { sum sqrt(d^2 + eps), sum pred, sum pred^2, sum target^2, sum d^2 };
+ * d_pred (optional) = d / sqrt(d^2 + eps) / n, the gradient that seeds jat_dit_backward. */
+int jat_charbonnier_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats5, int64_t n, float eps,
+                         void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Long-audio chunk plumbing (infer_test_v3m2.py:340-406 chunk loop, :188-233 crossfade_chunks).

@@ -71,7 +71,7 @@ class DitWeights(C.Structure):
         ("hidden", C.c_int32), ("depth", C.c_int32), ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32),
         ("head_dim", C.c_int32), ("mlp_hidden", C.c_int32), ("bottleneck", C.c_int32), ("channels", C.c_int32),
         ("patch_len", C.c_int32), ("norm_kind", C.c_int32), ("max_len", C.c_int32), ("rope_max_pos", C.c_int32),
-        ("norm_eps", C.c_float), ("reserved", C.c_int32),
+        ("norm_eps", C.c_float), ("cond_channels", C.c_int32),
         ("pe_w1", C.c_void_p), ("pe_b1", C.c_void_p), ("pe_w2", C.c_void_p), ("pe_b2", C.c_void_p),
         ("te_w1", C.c_void_p), ("te_b1", C.c_void_p), ("te_w2", C.c_void_p), ("te_b2", C.c_void_p),
         ("ada_w", C.c_void_p), ("ada_b", C.c_void_p),
@@ -135,6 +135,7 @@ SIGNATURES = {
     "jat_profile_end": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "jat_adaln_norm_modulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _f, _i, _i, _i, _vp]),
     "jat_patchify_cast": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "jat_patchify_cast2": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "jat_timestep_features": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "jat_gemm_bf16": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _i, _vp]),
     "jat_gqa_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -150,6 +151,7 @@ SIGNATURES = {
     "jat_grad_decompress": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "jat_train_inputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "jat_mse_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "jat_charbonnier_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, _vp]),
     "jat_chunk_normalize": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "jat_crossfade_denorm": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "jat_patchify_single": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

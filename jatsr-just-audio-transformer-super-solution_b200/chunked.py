@@ -105,7 +105,7 @@ def sample_long(model, lr_latent, lr_mean=None, lr_std=None, hr_mean=None, hr_st
     import torch.distributed as dist
     device = torch.device(device)
     lr_latent = lr_latent.to(device=device, dtype=torch.float32)
-    Cc = lr_latent.shape[0]
+    Cc = getattr(model, "input_channels", lr_latent.shape[0])   # channels of the GENERATED latent (= the condition's in the reference's configs)
     total = lr_latent.shape[-1] if total_frames is None else min(total_frames, lr_latent.shape[-1])
     plan = plan_chunks(total, chunk_frames, overlap_frames)
     stride = chunk_frames - overlap_frames

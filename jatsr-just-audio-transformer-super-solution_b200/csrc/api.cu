@@ -676,19 +676,24 @@ static int adaln_norm_modulate_stats(jat_ctx* ctx, const float* x, void* out_bf1
 }
 
 // ------------------------------------------------------------------------------------------------ misc
-extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
-                                 void* out_bf16, int B, int C, int T, int P, void* stream) {
+extern "C" int jat_patchify_cast2(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
+                                  void* out_bf16, int B, int C, int Cc, int T, int P, void* stream) {
     DeviceGuard dev_guard__(ctx);
     if (!ctx || !x_t || !out_bf16) return fail(JAT_ERR_BAD_ARG, "jat_patchify_cast: null argument");
     if (P != 4) return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: patch_len must be 4 (got %d)", P);
-    if (B <= 0 || C <= 0 || T <= 0 || C % PATCH_TC != 0 || xt_batch <= 0 || B > 65535)
-        return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: need C %% 32 == 0, 0 < B <= 65535");
+    if (B <= 0 || C <= 0 || Cc <= 0 || T <= 0 || C % PATCH_TC != 0 || Cc % PATCH_TC != 0 || xt_batch <= 0 || B > 65535)
+        return fail(JAT_ERR_BAD_SHAPE, "jat_patchify_cast: need C %% 32 == 0, Cc %% 32 == 0, 0 < B <= 65535");
     const int N = (T + P - 1) / P;
-    dim3 grid((N + PATCH_TN - 1) / PATCH_TN, 2 * C / PATCH_TC, B);
+    dim3 grid((N + PATCH_TN - 1) / PATCH_TN, (C + Cc) / PATCH_TC, B);
     pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
     launch_pdl(patchify_cast_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x_t, xt_batch, x_cond, cond_batch,
-               (__nv_bfloat16*)out_bf16, C, T, N, 2 * C * 4);
+               (__nv_bfloat16*)out_bf16, C, Cc, T, N, (C + Cc) * 4);
     return post_launch(ctx, "patchify_cast");
+}
+
+extern "C" int jat_patchify_cast(jat_ctx* ctx, const float* x_t, int xt_batch, const float* x_cond, int cond_batch,
+                                 void* out_bf16, int B, int C, int T, int P, void* stream) {
+    return jat_patchify_cast2(ctx, x_t, xt_batch, x_cond, cond_batch, out_bf16, B, C, C, T, P, stream);
 }
 
 extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int C, int T, int P, void* stream) {
@@ -700,7 +705,7 @@ extern "C" int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16,
     dim3 grid((N + PATCH_TN - 1) / PATCH_TN, C / PATCH_TC, B);
     pre_launch(ctx, TAG_PATCHIFY, (cudaStream_t)stream);
     launch_pdl(patchify_cast_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, B, (const float*)nullptr, 0,
-               (__nv_bfloat16*)out_bf16, C, T, N, C * 4);
+               (__nv_bfloat16*)out_bf16, C, 0, T, N, C * 4);
     return post_launch(ctx, "patchify_single");
 }
 
@@ -923,20 +928,33 @@ extern "C" int jat_train_inputs(jat_ctx* ctx, const float* hr, const float* lr, 
     return post_launch(ctx, "train_inputs");
 }
 
-extern "C" int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n,
-                            void* stream) {
-    DeviceGuard dev_guard__(ctx);
-    if (!ctx || !pred || !target || !stats4 || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: bad argument");
+static int recon_loss(jat_ctx* ctx, int kind, const float* pred, const float* target, float* d_pred, double* stats, int64_t n,
+                      float eps, void* stream) {
+    if (!ctx || !pred || !target || !stats || n <= 0) return fail(JAT_ERR_BAD_ARG, "jat_mse_loss / jat_charbonnier_loss: bad argument");
     if ((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)d_pred) & 15) != 0)
-        return fail(JAT_ERR_BAD_ARG, "jat_mse_loss: tensors must be 16-byte aligned");
+        return fail(JAT_ERR_BAD_ARG, "jat_mse_loss / jat_charbonnier_loss: tensors must be 16-byte aligned");
+    if (kind == 1 && !(eps > 0.0f)) return fail(JAT_ERR_BAD_ARG, "jat_charbonnier_loss: eps must be positive");
     cudaStream_t s = (cudaStream_t)stream;
-    JAT_CUDA(cudaMemsetAsync(stats4, 0, 4 * sizeof(double), s));
+    JAT_CUDA(cudaMemsetAsync(stats, 0, (kind == 0 ? 4 : 5) * sizeof(double), s));
     long long want = (n / 4 + 255) / 256;
     const long long cap = (long long)ctx->sm_count * 8;
     const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     pre_launch(ctx, TAG_TRAIN_GLUE, s);
-    mse_loss_kernel<<<blocks, 256, 0, s>>>(pred, target, d_pred, stats4, (long long)n, (float)(2.0 / (double)n));
-    return post_launch(ctx, "mse_loss");
+    if (kind == 0) recon_loss_kernel<0><<<blocks, 256, 0, s>>>(pred, target, d_pred, stats, (long long)n, (float)(2.0 / (double)n), 0.0f);
+    else recon_loss_kernel<1><<<blocks, 256, 0, s>>>(pred, target, d_pred, stats, (long long)n, (float)(1.0 / (double)n), eps);
+    return post_launch(ctx, kind == 0 ? "mse_loss" : "charbonnier_loss");
+}
+
+extern "C" int jat_mse_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats4, int64_t n,
+                            void* stream) {
+    DeviceGuard dev_guard__(ctx);
+    return recon_loss(ctx, 0, pred, target, d_pred, stats4, n, 0.0f, stream);
+}
+
+extern "C" int jat_charbonnier_loss(jat_ctx* ctx, const float* pred, const float* target, float* d_pred, double* stats5, int64_t n,
+                                    float eps, void* stream) {
+    DeviceGuard dev_guard__(ctx);
+    return recon_loss(ctx, 1, pred, target, d_pred, stats5, n, eps, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer step
@@ -1235,10 +1253,11 @@ extern "C" int jat_dit_forward_tokens(jat_ctx* ctx, const jat_dit_weights* w, co
     if (w->head_dim != 64) return fail(JAT_ERR_BAD_SHAPE, "head_dim must be 64");
     const int M = B * N;
     const int QKV = (w->n_q_heads + 2 * w->n_kv_heads) * 64;
-    const int KIN = 2 * C * P;
+    const int Cc = w->cond_channels > 0 ? w->cond_channels : C;
+    const int KIN = (C + Cc) * P;
     cudaStream_t s = (cudaStream_t)stream;
 
-    JAT_TRY(jat_patchify_cast(ctx, x_t, xt_batch, x_cond, cond_batch, ws->patches, B, C, T, P, stream));
+    JAT_TRY(jat_patchify_cast2(ctx, x_t, xt_batch, x_cond, cond_batch, ws->patches, B, C, Cc, T, P, stream));
     jat_gemm_epilogue e = epi_bias_act(w->pe_b1, ws->pe_hid, BD, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16);
     JAT_TRY(jat_gemm_bf16(ctx, ws->patches, KIN, w->pe_w1, KIN, M, BD, KIN, &e, -1, 0, stream));
     e = epi_bias_act(w->pe_b2, ws->x, D, JAT_ACT_NONE, JAT_DTYPE_F32);
@@ -1301,7 +1320,8 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
     if (N > w->max_len) return fail(JAT_ERR_SEQ_TOO_LONG, "Sequence length %d exceeds max_len %d", N, w->max_len);
     if (w->head_dim != 64) return fail(JAT_ERR_BAD_SHAPE, "head_dim must be 64");
     const int M = B * N, Hq = w->n_q_heads, Hkv = w->n_kv_heads;
-    const int QKV = (Hq + 2 * Hkv) * 64, KIN = 2 * C * P, NM = w->depth * 6 * D;
+    const int Cc = w->cond_channels > 0 ? w->cond_channels : C;
+    const int QKV = (Hq + 2 * Hkv) * 64, KIN = (C + Cc) * P, NM = w->depth * 6 * D;
     cudaStream_t s = (cudaStream_t)stream;
     jat_gemm_epilogue e;
     // ---- train-mode regularisers: Dropout(p) on attention probabilities / GELU output / mlp.3 output, DropPath per block
@@ -1324,7 +1344,7 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
     JAT_TRY(jat_gemm_bf16(ctx, ws->t_act, D, w->ada_w, D, B, NM, D, &e, -1, 0, stream));
 
     // ---- patch embed
-    JAT_TRY(jat_patchify_cast(ctx, x_t, B, x_cond, B, ws->patches, B, C, T, P, stream));
+    JAT_TRY(jat_patchify_cast2(ctx, x_t, B, x_cond, B, ws->patches, B, C, Cc, T, P, stream));
     e = epi_bias_act(w->pe_b1, ws->pe_hid, BD, JAT_ACT_GELU_ERF, JAT_DTYPE_BF16); e.aux = sv->pe_u; e.ld_aux = BD;
     JAT_TRY(jat_gemm_bf16(ctx, ws->patches, KIN, w->pe_w1, KIN, M, BD, KIN, &e, -1, 0, stream));
     e = epi_bias_act(w->pe_b2, ws->x, D, JAT_ACT_NONE, JAT_DTYPE_F32);
@@ -1418,7 +1438,8 @@ static BwdDims bwd_dims(const jat_dit_weights* w, int B, int T) {
     BwdDims d;
     d.D = w->hidden; d.P = w->patch_len; d.C = w->channels; d.F = w->mlp_hidden; d.BD = w->bottleneck;
     d.N = (T + d.P - 1) / d.P; d.M = B * d.N; d.Hq = w->n_q_heads; d.Hkv = w->n_kv_heads;
-    d.QKV = (d.Hq + 2 * d.Hkv) * 64; d.KIN = 2 * d.C * d.P; d.SIXD = 6 * d.D; d.CP = d.C * d.P;
+    d.QKV = (d.Hq + 2 * d.Hkv) * 64; d.KIN = (d.C + (w->cond_channels > 0 ? w->cond_channels : d.C)) * d.P;
+    d.SIXD = 6 * d.D; d.CP = d.C * d.P;
     d.MD = (int64_t)d.M * d.D;
     return d;
 }

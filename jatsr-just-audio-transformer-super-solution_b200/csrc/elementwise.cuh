@@ -101,7 +101,7 @@ adaln_norm_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Patchify + channel concat + zero pad + f32->bf16 cast (jat_audiosr_v2.py:411-421, 225-227).
-//   out[b*N + n, c*4 + p] = src[b', c, 4n + p]     src = x_t for c < C, x_cond for c >= C
+//   out[b*N + n, c*4 + p] = src[b', c, 4n + p]     src = x_t for c < C, x_cond (Cc channels) for C <= c < C + Cc
 // Tile = 32 channels x 32 tokens: coalesced f32 reads along T into shared memory, then each warp
 // writes 32 channels x 4 = 128 contiguous bf16 (256 B) of one token row.
 // ------------------------------------------------------------------------------------------------
@@ -111,18 +111,18 @@ constexpr int PATCH_ROW = PATCH_TN * 4 + 4;  // padded smem row (floats)
 
 __global__ void __launch_bounds__(256)
 patchify_cast_kernel(const float* __restrict__ x_t, int xt_batch, const float* __restrict__ x_cond, int cond_batch,
-                     __nv_bfloat16* __restrict__ out, int C, int T, int N, int K) {
+                     __nv_bfloat16* __restrict__ out, int C, int Cc, int T, int N, int K) {
     __shared__ __align__(16) float tile[PATCH_TC][PATCH_ROW];
     pdl_wait();  // (no early launch_dependents: the successor's CTAs would take occupancy from this grid's later waves)
     const int n0 = blockIdx.x * PATCH_TN;
-    const int c0 = blockIdx.y * PATCH_TC;  // in [0, 2C)
+    const int c0 = blockIdx.y * PATCH_TC;  // in [0, C + Cc): x_t channels first, then the Cc condition channels
     const int b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const bool is_cond = c0 >= C;
     const float* src = nullptr;
     if (!is_cond) src = x_t + ((long long)(b % xt_batch) * C + c0) * T;
-    else if (x_cond != nullptr && b < cond_batch) src = x_cond + ((long long)b * C + (c0 - C)) * T;
+    else if (x_cond != nullptr && b < cond_batch) src = x_cond + ((long long)b * Cc + (c0 - C)) * T;
 
     const int t0 = n0 * 4;
 #pragma unroll

@@ -1,7 +1,7 @@
 // The elementwise work either side of the model call in the training step:
 //   train_inputs_kernel   normalise + conditional-noise augmentation + CFG condition dropout + flow-matching mix
 //                         (train_ddp_v3mod2.py:856-883, train_ddp_v3m2.py:547-580) in ONE pass over the batch
-//   mse_loss_kernel       x-prediction MSE (train_ddp_v3mod2.py:889) with its gradient seed and the monitoring sums
+//   recon_loss_kernel     x-prediction MSE / Charbonnier (train_ddp_v3mod2.py:889) with its gradient seed and the monitoring sums
 //                         (:900-911: pred mean / std, signal and noise power for the SNR) in ONE pass
 // HBM-bound, 128-bit accesses.  All arithmetic is unfused round-to-nearest fp32 in the reference's order, so the three
 // outputs of train_inputs are bit-identical to the torch expressions.
@@ -54,38 +54,43 @@ train_inputs_kernel(const float* __restrict__ hr, const float* __restrict__ lr, 
     }
 }
 
-// stats[0] += sum (pred - target)^2   stats[1] += sum pred   stats[2] += sum pred^2   stats[3] += sum target^2   (double)
-// d_pred = (pred - target) * scale  with scale = 2 / n  (the gradient of mean((pred - target)^2)), if d_pred != NULL
+// LOSS = 0 (MSE, train_ddp_v3mod2.py:889):
+//   stats[0] += sum (pred - target)^2   stats[1] += sum pred   stats[2] += sum pred^2   stats[3] += sum target^2   (double)
+//   d_pred = (pred - target) * scale  with scale = 2 / n  (the gradient of mean((pred - target)^2)), if d_pred != NULL
+// LOSS = 1 (Charbonnier, train_ddp_v3mod3.py:57-85: mean(sqrt((pred - target)^2 + eps))):
+//   stats[0] += sum sqrt(d^2 + eps), stats[1..3] as above, stats[4] += sum d^2 (the SNR monitor still needs it);
+//   d_pred = d / sqrt(d^2 + eps) * scale  with scale = 1 / n
+template <int LOSS>
 __global__ void __launch_bounds__(256)
-mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ d_pred, double* __restrict__ stats,
-                long long n, float scale) {
-    float se = 0.f, sp = 0.f, spp = 0.f, stt = 0.f;
+recon_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ d_pred, double* __restrict__ stats,
+                  long long n, float scale, float eps) {
+    float sl = 0.f, sp = 0.f, spp = 0.f, stt = 0.f, se = 0.f;
+    auto one = [&](float p, float q) -> float {
+        const float d = p - q;
+        sp += p; spp += p * p; stt += q * q;
+        if constexpr (LOSS == 0) { sl += d * d; return d * scale; }
+        else { const float r = sqrtf(d * d + eps); sl += r; se += d * d; return d / r * scale; }
+    };
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     for (; i + 3 < n; i += stride) {
         const float4 p = __ldcs(reinterpret_cast<const float4*>(pred + i));
         const float4 q = __ldcs(reinterpret_cast<const float4*>(target + i));
-        const float4 d = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
-        se += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-        sp += p.x + p.y + p.z + p.w;
-        spp += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
-        stt += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-        if (d_pred != nullptr)
-            *reinterpret_cast<float4*>(d_pred + i) = make_float4(d.x * scale, d.y * scale, d.z * scale, d.w * scale);
+        const float4 g = make_float4(one(p.x, q.x), one(p.y, q.y), one(p.z, q.z), one(p.w, q.w));
+        if (d_pred != nullptr) *reinterpret_cast<float4*>(d_pred + i) = g;
     }
     if (i < n && i + 3 >= n) {  // ragged tail (n % 4 != 0): handled by the one thread that lands on it
         for (long long j = i; j < n; ++j) {
-            const float p = pred[j], q = target[j], d = p - q;
-            se += d * d; sp += p; spp += p * p; stt += q * q;
-            if (d_pred != nullptr) d_pred[j] = d * scale;
+            const float g = one(pred[j], target[j]);
+            if (d_pred != nullptr) d_pred[j] = g;
         }
     }
-    se = warp_sum(se); sp = warp_sum(sp); spp = warp_sum(spp); stt = warp_sum(stt);
-    __shared__ float red[4][8];
+    sl = warp_sum(sl); sp = warp_sum(sp); spp = warp_sum(spp); stt = warp_sum(stt); se = warp_sum(se);
+    __shared__ float red[5][8];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { red[0][w] = se; red[1][w] = sp; red[2][w] = spp; red[3][w] = stt; }
+    if (l == 0) { red[0][w] = sl; red[1][w] = sp; red[2][w] = spp; red[3][w] = stt; red[4][w] = se; }
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < (LOSS == 0 ? 4 : 5)) {
         double s = 0.0;
         for (int k = 0; k < 8; ++k) s += (double)red[threadIdx.x][k];
         atomicAdd(stats + threadIdx.x, s);

@@ -109,6 +109,7 @@ class PackedWeights:
         w.mlp_hidden = model.blocks[0].mlp[0].out_features
         w.bottleneck = model.patch_embed.proj[0].out_features
         w.channels, w.patch_len = model.input_channels, model.patch_len
+        w.cond_channels = model.cond_channels
         w.norm_kind, w.max_len, w.rope_max_pos = model.norm_kind, model.max_len, rope.max_seq_len
         w.norm_eps = 1e-6
         p = lambda t: t.data_ptr()
@@ -262,7 +263,7 @@ class Workspace:
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
         self.B, self.T, self.Bt, self.N, self.M = B, T, Bt, N, M
         self.buf = dict(
-            patches=bf(M, 2 * Cc * P), pe_hid=bf(M, w.patch_embed.proj[0].out_features), x=f32(M, D), h=bf(M, D),
+            patches=bf(M, (Cc + w.cond_channels) * P), pe_hid=bf(M, w.patch_embed.proj[0].out_features), x=f32(M, D), h=bf(M, D),
             qkv=bf(M, qkv), attn=bf(M, D), mlp_hid=bf(M, F),
             t_feat=bf(Bt, D), t_hid=bf(Bt, D), t_act=bf(Bt, D), mod=f32(Bt, depth * 6 * D),
         )

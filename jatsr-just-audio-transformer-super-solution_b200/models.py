@@ -221,11 +221,10 @@ class _JaTBase(nn.Module):
     def _check_inputs(self, x_t, t, x_cond):
         if not (x_t.is_cuda and x_cond.is_cuda and t.is_cuda):
             raise RuntimeError("jat_b200 models run on CUDA (sm_100a) tensors only; there is no CPU fallback")
-        if x_t.dim() != 3 or x_t.shape != x_cond.shape or x_t.shape[1] != self.input_channels:
-            raise ValueError(f"expected x_t/x_cond [B, {self.input_channels}, T], got {tuple(x_t.shape)} / "
-                             f"{tuple(x_cond.shape)}")
-        if self.cond_channels != self.input_channels:
-            raise NotImplementedError("cond_channels != input_channels is not supported by the fused patchify")
+        if (x_t.dim() != 3 or x_cond.dim() != 3 or x_t.shape[0] != x_cond.shape[0] or x_t.shape[2] != x_cond.shape[2]
+                or x_t.shape[1] != self.input_channels or x_cond.shape[1] != self.cond_channels):
+            raise ValueError(f"expected x_t [B, {self.input_channels}, T] and x_cond [B, {self.cond_channels}, T], got "
+                             f"{tuple(x_t.shape)} / {tuple(x_cond.shape)}")
         if t.dim() != 1 or t.shape[0] != x_t.shape[0]:
             raise ValueError("t must be [B]")
         if not 0.0 <= self.dropout_p < 1.0:
@@ -249,7 +248,7 @@ class _JaTBase(nn.Module):
         else:
             out = self._engine.forward(xt, tt, xc)
         if torch.is_autocast_enabled():
-            out = out.to(torch.get_autocast_gpu_dtype())
+            out = out.to(torch.get_autocast_dtype("cuda"))
         return out
 
     @torch.no_grad()

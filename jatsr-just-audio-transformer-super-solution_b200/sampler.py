@@ -30,14 +30,17 @@ class _Plan:
     """Buffers (+ optional captured graph) for one (model, B, C, T, steps, cfg) sampling problem."""
 
     def __init__(self, model, B, Cc, T, num_steps, cfg_scale, device):
+        """Cc = channels of the condition latent; the generated latent has model.input_channels (the reference draws z0
+        with the condition's shape, infer_test_v3m2.py:133 -- its configs have equal channel counts)."""
         self.key = (B, Cc, T, num_steps, float(cfg_scale), device)
+        Cz = model.input_channels
         self.use_cfg = cfg_scale != 1.0
         self.Beff = 2 * B if self.use_cfg else B
         eng = model._engine
         self.ws = eng.workspace(self.Beff, T, num_steps, device)
-        self.z = torch.empty(B, Cc, T, dtype=torch.float32, device=device)
+        self.z = torch.empty(B, Cz, T, dtype=torch.float32, device=device)
         self.lr = torch.empty(B, Cc, T, dtype=torch.float32, device=device)
-        self.x_pred = torch.empty(self.Beff, Cc, T, dtype=torch.float32, device=device)
+        self.x_pred = torch.empty(self.Beff, Cz, T, dtype=torch.float32, device=device)
         # timesteps exactly as the reference builds them (:136), on the same device
         ts = torch.linspace(0.0, 1.0, num_steps + 1, device=device)
         self.t_curr = ts[:-1].contiguous()
@@ -78,7 +81,9 @@ def flow_matching_sample(model, lr_latent, num_steps=50, cfg_scale=1.0, device="
     if model.training:
         raise RuntimeError("flow_matching_sample expects model.eval()")
     B, Cc, T = lr_latent.shape
-    z_init = torch.randn(B, Cc, T, device=device) if z0 is None else z0.to(device=device, dtype=torch.float32)
+    if Cc != model.cond_channels:
+        raise ValueError(f"expected lr_latent [B, {model.cond_channels}, T], got {tuple(lr_latent.shape)}")
+    z_init = torch.randn(B, model.input_channels, T, device=device) if z0 is None else z0.to(device=device, dtype=torch.float32)
     if use_graph is None:
         use_graph = os.environ.get("JAT_B200_GRAPH", "1") != "0"
 

@@ -4,6 +4,7 @@
                        augmentation, CFG condition dropout, flow-matching mix -- one kernel (`jat_train_inputs`)
   mse_loss        <->  F.mse_loss(pred_x0, hr_norm) (:889) + the monitoring sums of :900-911 -- one kernel
                        (`jat_mse_loss`) that also writes the gradient seed, so `loss.backward()` costs one scaling pass
+  charbonnier_loss <-> charbonnier_loss(pred_x0, hr_norm, eps) of the MOD3 script (train_ddp_v3mod3.py:57-85, :957)
 
 The random draws stay torch's (`torch.rand`, `torch.randn_like` from the global generators, like the reference), so a
 training script keeps its RNG stream; only the arithmetic moves into the library.
@@ -47,14 +48,19 @@ def prepare_inputs(hr, lr, hr_mean, hr_std, lr_mean, lr_std, t, noise, cond_nois
 
 class _MseLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target):
+    def forward(ctx, pred, target, charbonnier_eps=None):
         p = pred.float().contiguous()
         q = target.float().contiguous()
         need = pred.requires_grad
         d_pred = torch.empty_like(p) if need else None
-        stats = torch.empty(4, dtype=torch.float64, device=p.device)
-        L.check(L.load().jat_mse_loss(_ctx(p), p.data_ptr(), q.data_ptr(), _p(d_pred), stats.data_ptr(), p.numel(),
-                                      _stream(p.device)))
+        if charbonnier_eps is None:
+            stats = torch.empty(4, dtype=torch.float64, device=p.device)
+            L.check(L.load().jat_mse_loss(_ctx(p), p.data_ptr(), q.data_ptr(), _p(d_pred), stats.data_ptr(), p.numel(),
+                                          _stream(p.device)))
+        else:
+            stats = torch.empty(5, dtype=torch.float64, device=p.device)
+            L.check(L.load().jat_charbonnier_loss(_ctx(p), p.data_ptr(), q.data_ptr(), _p(d_pred), stats.data_ptr(), p.numel(),
+                                                  float(charbonnier_eps), _stream(p.device)))
         ctx.d_pred, ctx.in_dtype = d_pred, pred.dtype
         loss = (stats[0] / p.numel()).float()
         ctx.mark_non_differentiable(stats)
@@ -64,7 +70,7 @@ class _MseLoss(torch.autograd.Function):
     def backward(ctx, g_loss, _g_stats):
         d = ctx.d_pred
         ctx.d_pred = None
-        return (d * g_loss).to(ctx.in_dtype), None
+        return (d * g_loss).to(ctx.in_dtype), None, None
 
 
 def mse_loss(pred, target, return_stats=False):
@@ -72,4 +78,12 @@ def mse_loss(pred, target, return_stats=False):
     [sum sq err, sum pred, sum pred^2, sum target^2] from which the reference's monitoring values follow without extra
     passes or syncs: pred mean / std, SNR = 10 log10(sum target^2 / sum sq err) (train_ddp_v3mod2.py:900-911)."""
     loss, stats = _MseLoss.apply(pred, target)
+    return (loss, stats) if return_stats else loss
+
+
+def charbonnier_loss(pred, target, eps=1e-6, return_stats=False):
+    """mean(sqrt((pred - target)^2 + eps)) -- `charbonnier_loss` of the MOD3 training script (train_ddp_v3mod3.py:57-85) in
+    one pass with its gradient seed.  With return_stats also the device tensor (float64 [5]) [sum sqrt(d^2 + eps), sum pred,
+    sum pred^2, sum target^2, sum d^2] behind the script's monitoring values (:1031ff)."""
+    loss, stats = _MseLoss.apply(pred, target, float(eps))
     return (loss, stats) if return_stats else loss

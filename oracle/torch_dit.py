@@ -87,7 +87,8 @@ def dit_forward(p, cfg, x_t, t, x_cond, rms=False, masks=None, blocks_out=None, 
     pad = (P - T % P) % P
     x = torch.cat([F.pad(x_t, (0, pad)), F.pad(x_cond, (0, pad))], 1)
     N = x.shape[-1] // P
-    x = x.reshape(B, 2 * C, N, P).permute(0, 2, 1, 3).reshape(B, N, 2 * C * P)
+    Cin = x.shape[1]   # input_channels + cond_channels
+    x = x.reshape(B, Cin, N, P).permute(0, 2, 1, 3).reshape(B, N, Cin * P)
     x = F.gelu(x @ p["patch_embed.proj.0.weight"].T + p["patch_embed.proj.0.bias"])
     x = x @ p["patch_embed.proj.2.weight"].T + p["patch_embed.proj.2.bias"]
     half = D // 2

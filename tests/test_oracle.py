@@ -77,6 +77,9 @@ REF_CASES = [
              num_kv_heads=2, bottleneck_dim=64, mlp_ratio=2.0), 2, 517),
     (0, dict(input_channels=64, cond_channels=64, patch_len=4, hidden_size=320, depth=2, num_q_heads=5,
              num_kv_heads=1, bottleneck_dim=64), 2, 88),
+    # condition latent with its own channel count (constructor contract, jat_audiosr_v2.py:297-308)
+    (1, dict(input_channels=32, cond_channels=96, patch_len=4, hidden_size=256, depth=2, num_q_heads=4,
+             num_kv_heads=2, bottleneck_dim=64), 2, 171),
 ]
 
 
@@ -92,7 +95,7 @@ def test_oracle_matches_reference_module(case):
     rerandomise_zero_init(model, seed=case + 1, bf16_exact=False)
     g = torch.Generator().manual_seed(100 + case)
     x_t = torch.randn(B, cfg["input_channels"], T, generator=g)
-    cond = torch.randn(B, cfg["input_channels"], T, generator=g)
+    cond = torch.randn(B, cfg["cond_channels"], T, generator=g)
     t = torch.rand(B, generator=g)
     with torch.no_grad():
         want = model(x_t, t, cond).numpy()
@@ -101,6 +104,12 @@ def test_oracle_matches_reference_module(case):
     assert np.abs(want).max() > 0.05
     assert np.abs(got - want).max() < 3e-5
     assert rel_l2(got, want) < 1e-5
+    # the torch restatement (fp32 truth of the GPU parity tests) on the same case
+    from tests._torch_dit import dit_forward
+    with torch.no_grad():
+        got_t = dit_forward({k: v.detach() for k, v in model.state_dict().items()}, dict(cfg, patch_len=cfg.get("patch_len", 4)),
+                            x_t, t, cond, rms=(cls_idx == 1)).numpy()
+    assert rel_l2(got_t, want) < 1e-5
 
 
 @pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")

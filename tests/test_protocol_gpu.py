@@ -94,7 +94,9 @@ def test_eval_forward_between_train_forward_and_backward_is_harmless():
         model(torch.randn_like(z_t), 1.0 - t, torch.randn_like(lr))    # train mode without grad = plain forward, too
     loss.backward()
     for p, w in zip(model.parameters(), want):
-        assert ((p.grad - w).norm() / w.norm().clamp_min(1e-20)).item() < 1e-5
+        # (run-to-run differences: f32 reduce-add order of the split-K weight gradients and the column sums; a clobbered
+        #  workspace gives errors of order one)
+        assert ((p.grad - w).norm() / w.norm().clamp_min(1e-20)).item() < 2e-4
 
 
 def test_sampler_reuses_plan_and_graph_with_unindexed_device():

@@ -239,3 +239,22 @@ def test_fused_mse_loss_matches_torch(n_shape):
     snr = 10 * np.log10(s[3] / s[0])                                                   # :905-908
     want_snr = (10 * torch.log10((target ** 2).mean() / (((pred - target) ** 2).mean() + 1e-8))).item()
     assert abs(snr - want_snr) < 1e-3
+
+
+@pytest.mark.parametrize("n_shape", [(4, 64, 1378), (1, 3, 7)])
+def test_fused_charbonnier_loss_matches_reference_expression(n_shape):
+    """train_ddp_v3mod3.py:57-85: loss = sqrt((pred - target)^2 + eps).mean(); value and gradient against torch autograd."""
+    from jat_b200 import training
+    g = torch.Generator(device=dev()).manual_seed(8)
+    pred = torch.randn(*n_shape, generator=g, device=dev()).requires_grad_(True)
+    target = torch.randn(*n_shape, generator=g, device=dev())
+    target[..., :2] = pred.detach()[..., :2]                 # exact zeros of the residual: the eps branch
+    loss, stats = training.charbonnier_loss(pred, target, eps=1e-6, return_stats=True)
+    (loss * 2.0).backward()
+    p2 = pred.detach().clone().requires_grad_(True)
+    want = torch.sqrt((p2 - target) ** 2 + 1e-6).mean()
+    (want * 2.0).backward()
+    assert abs(loss.item() - want.item()) <= 3e-6 * abs(want.item())
+    assert rel_l2(pred.grad.cpu().numpy(), p2.grad.cpu().numpy()) < 1e-6
+    s = stats.cpu().numpy()
+    assert abs(s[4] / pred.numel() - ((pred - target) ** 2).mean().item()) < 1e-5
