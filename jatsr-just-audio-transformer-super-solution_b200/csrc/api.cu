@@ -153,7 +153,13 @@ extern "C" int jat_create(int device, jat_ctx** out) {
     c->att_trace = nullptr;
     c->tail_ws = nullptr;
     c->tail_cnt = nullptr;
-    c->tail_split = getenv("JAT_GEMM_TAIL") ? atoi(getenv("JAT_GEMM_TAIL")) : 0;
+    // default 2: the tiles of a partial last wave of the inference out_proj / fc2 GEMMs are cut along K and every part reduce-adds
+    // its partial sum into the residual stream (gate-residual class 0.84 -> 0.91 of the sustained bf16 peak); the f32 adds of
+    // one tile's parts land in arrival order, i.e. ~3 % of the output tiles can differ in the last bit from run to run (and,
+    // through the bf16 rounding of the next GEMM operand, the model output by a few 1e-5 relative).
+    // JAT_GEMM_TAIL=0 / jat_set_gemm_tail_split(ctx, 0) / torch.use_deterministic_algorithms(True) (honoured by the Python
+    // engine) give the bit-reproducible schedule.
+    c->tail_split = getenv("JAT_GEMM_TAIL") ? atoi(getenv("JAT_GEMM_TAIL")) : 2;
     if (c->tail_split < 0 || c->tail_split > 2) c->tail_split = 0;
     c->gemm_trace = nullptr;
     const size_t cnt_bytes = (size_t)c->sm_count * GEMM_EPI_WARPS * sizeof(int);

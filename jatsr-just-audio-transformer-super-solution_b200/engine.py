@@ -332,8 +332,22 @@ class Engine:
                                        torch.cuda.current_stream(dev).cuda_stream))
         return ws.mod
 
+    _det_mode = {}   # device index -> deterministic flag last pushed into that device's context
+
+    @classmethod
+    def _sync_determinism(cls, idx):
+        """torch.use_deterministic_algorithms(True) selects the bit-reproducible GEMM schedule (no tail split); switching it
+        off again restores the library default (JAT_GEMM_TAIL or 2, see jat_create)."""
+        det = torch.are_deterministic_algorithms_enabled()
+        if cls._det_mode.get(idx, False) != det:
+            import os
+            mode = 0 if det else int(os.environ.get("JAT_GEMM_TAIL", "2"))
+            L.check(L.load().jat_set_gemm_tail_split(L.context(idx), mode))
+            cls._det_mode[idx] = det
+
     def forward_tokens(self, ws, x_t, x_cond, B, mod, mod_batch_stride, out, cond_batch=None):
         dev = x_t.device
+        self._sync_determinism(self._dev_index(dev))
         lib, ctx = L.load(), L.context(self._dev_index(dev))
         pw = self.weights(dev)
         T = x_t.shape[-1]
@@ -366,6 +380,7 @@ class Engine:
         blocks); they are stored next to the saved activations so that the backward regenerates the same masks."""
         B, Cc, T = x_t.shape
         dev = x_t.device
+        self._sync_determinism(self._dev_index(dev))
         lib, ctx = L.load(), L.context(self._dev_index(dev))
         pw = self.weights(dev)
         tb = self.train_buffers(B, T, dev)

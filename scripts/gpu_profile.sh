@@ -2,7 +2,7 @@
 # ncu evidence for the step: launch list (per-launch device time) + one `--set full` capture of the hot
 # kernels.  Run ONLY after the same bench command exited 0 without ncu (done first, below).
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --sub none"
 K="regex:gemm_tcgen05_kernel|gqa_attention_fwd_kernel|adaln_norm_modulate_kernel|patchify_cast_kernel|cfg_euler_update_kernel|timestep_features_kernel"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 420 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
