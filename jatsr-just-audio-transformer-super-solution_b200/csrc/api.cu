@@ -479,6 +479,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     if ((K % 64 != 0 && !(a_mn && w_mn)) || N % 128 != 0)
         return fail(JAT_ERR_BAD_SHAPE, "jat_gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
     const bool auto_cfg = cta_pair < 0 && block_n == 0 && ctx->gemm_block_n == 0 && ctx->gemm_cta_pair == 1 && !(a_mn && w_mn);
+    int auto_ks = 0;   // split-K factor chosen by the small-M model below (0: the caller's)
     if (cta_pair < 0) cta_pair = ctx->gemm_cta_pair;
     if (block_n == 0) block_n = ctx->gemm_block_n;
     if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
@@ -489,20 +490,29 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
         // k-block + epilogue); small tiles pay ~15 % (128-wide: operand stream per FLOP doubles) / ~10 % (single CTA: no
         // W-tile sharing).  The default is kept unless a candidate is at least 20 % cheaper -- large problems never switch.
         const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
-        const int ks = e->k_splits > 1 ? e->k_splits : 1;
-        auto cost = [&](int cg_, int bn_) -> double {
+        const int ks0 = e->k_splits > 1 ? e->k_splits : 1;
+        // split-K is offered to the inference gate-residual GEMMs (out_proj / fc2 at small M: one tile's K loop IS the
+        // launch) under the same policy as the tail split: allowed unless the bit-reproducible schedule was asked for
+        // (the parts' f32 adds into the residual stream land in arrival order)
+        const bool may_split = ks0 == 1 && ctx->tail_split == 2 && e->kind == JAT_EPI_GATE_RESIDUAL && e->aux == nullptr &&
+                               !(e->drop_p > 0.0f) && !w_mn;
+        auto cost = [&](int cg_, int bn_, int ks) -> double {
             const long long items = (long long)((M + 128 * cg_ - 1) / (128 * cg_)) * (N / bn_) * ks;
             const long long workers = ctx->gemm_sms / cg_;
             const long long rounds = (items + workers - 1) / workers;
             const double kb_clk = 2.0 * bn_ * (bn_ == 128 ? 1.15 : 1.0) * (cg_ == 1 ? 1.10 : 1.0);
             return (double)rounds * ((double)((kblocks + ks - 1) / ks) * kb_clk + 8.0 * bn_);
         };
-        const double base = cost(2, 256);
+        const double base = cost(2, 256, ks0);
         double best = base * 0.8;
-        const int cand[3][2] = {{2, 128}, {1, 256}, {1, 128}};
-        for (int i = 0; i < 3; ++i) {
-            const double c = cost(cand[i][0], cand[i][1]);
-            if (c < best) { best = c; cta_pair = cand[i][0] == 2 ? 1 : 0; block_n = cand[i][1]; }
+        const int cand[4][2] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
+        for (int i = 0; i < 4; ++i) {
+            for (int ks = ks0; ks <= (may_split ? 4 : ks0); ++ks) {
+                if (i == 0 && ks == ks0) continue;   // the default itself
+                if (ks > 1 && kblocks / ks < 8) break;
+                const double c = cost(cand[i][0], cand[i][1], ks);
+                if (c < best) { best = c; cta_pair = cand[i][0] == 2 ? 1 : 0; block_n = cand[i][1]; auto_ks = ks; }
+            }
         }
     }
     if (block_n != 128 && block_n != 256) return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: block_n must be 128 or 256");
@@ -538,7 +548,7 @@ extern "C" int jat_gemm_bf16(jat_ctx* ctx, const void* A, int64_t lda, const voi
     p.t_out = e->t_out;
     p.aux = e->aux;
     p.ld_aux = e->ld_aux;
-    p.k_splits = e->k_splits > 1 ? e->k_splits : 1;
+    p.k_splits = auto_ks > 0 ? auto_ks : (e->k_splits > 1 ? e->k_splits : 1);
     if (p.k_splits > 1 && e->kind != JAT_EPI_GATE_RESIDUAL && e->kind != JAT_EPI_ACCUM)
         return fail(JAT_ERR_BAD_ARG, "jat_gemm_bf16: k_splits needs a reduce-add epilogue (GATE_RESIDUAL / ACCUM)");
     if (p.k_splits > p.num_k_blocks) p.k_splits = p.num_k_blocks;
