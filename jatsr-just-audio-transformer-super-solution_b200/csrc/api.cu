@@ -353,18 +353,18 @@ extern "C" int jat_drop_path_scales(jat_ctx* ctx, float* out, const float* rates
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1>
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1, int EW = GEMM_EPI_WARPS>
 static int launch_gemm(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                        const GemmParams& p, cudaStream_t s) {
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN, MC>;
+    auto kern = gemm_tcgen05_kernel<BN, CG, EPI, ACT, OUT_BF16, A_MN, B_MN, MC, EW>;
     JAT_TRY(ensure_dyn_smem(ctx, (const void*)kern, Cfg::SMEM_BYTES));
     int clusters = ctx->gemm_sms / (CG * MC);
     const int num_work = p.head_tiles * p.k_splits + (p.num_tiles - p.head_tiles) * p.tail_splits;
     if (clusters > num_work) clusters = num_work;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG * MC));
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(128 + EW * 32);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -421,6 +421,16 @@ static int dispatch_gemm_mc2(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
                 e->out_dtype);
 }
 
+// 16 epilogue warps (see gemm_tcgen05_kernel) for the bias + GELU epilogue: JAT_GEMM_EW16 selects when -- 0 never, 1 when the
+// epilogue carries the training extras (pre-activation copy or dropout: ~33 instructions per element; fc1 forward of the
+// training step 135 -> 113 us, class 8.75 -> 8.14 ms per step), 2 always.
+// Not combined with the workspace tail split (its per-warp regions are laid out for 8 warps).
+static bool gemm_ew16(const GemmParams& p) {
+    static const int mode = getenv("JAT_GEMM_EW16") ? atoi(getenv("JAT_GEMM_EW16")) : 1;
+    if (mode <= 0 || (p.tail_splits > 1 && !p.tail_direct)) return false;
+    return mode >= 2 || p.aux != nullptr || p.drop.thresh != 0u;
+}
+
 template <int BN, int CG>
 static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                              const GemmParams& p, const jat_gemm_epilogue* e, cudaStream_t s) {
@@ -440,6 +450,8 @@ static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
             case JAT_EPI_ACCUM:
                 return launch_gemm<BN, CG, EPI_ACCUM, ACT_NONE, 0, 0, 1>(ctx, ta, tb, to, p, s);
             case JAT_EPI_DACT:
+                // (16 epilogue warps were measured SLOWER for this epilogue: 141.7 vs 132.8 us -- its 64 pre-activation values
+                //  per thread do not fit the 96-register budget next to the accumulator half; it stays on 8 warps)
                 if (e->act == JAT_ACT_GELU_ERF) return launch_gemm<BN, CG, EPI_DACT, ACT_GELU, 1, 0, 1>(ctx, ta, tb, to, p, s);
                 if (e->act == JAT_ACT_SILU) return launch_gemm<BN, CG, EPI_DACT, ACT_SILU, 1, 0, 1>(ctx, ta, tb, to, p, s);
                 break;
@@ -454,6 +466,10 @@ static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
                 return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 0>(ctx, ta, tb, to, p, s);
             if (e->act == JAT_ACT_NONE && e->out_dtype == JAT_DTYPE_BF16)
                 return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_NONE, 1>(ctx, ta, tb, to, p, s);
+            if constexpr (BN == 256 && CG == 2) {
+                if (e->act == JAT_ACT_GELU_ERF && e->out_dtype == JAT_DTYPE_BF16 && gemm_ew16(p))
+                    return launch_gemm<256, 2, EPI_BIAS_ACT, ACT_GELU, 1, 0, 0, 1, 16>(ctx, ta, tb, to, p, s);
+            }
             if (e->act == JAT_ACT_GELU_ERF && e->out_dtype == JAT_DTYPE_BF16)
                 return launch_gemm<BN, CG, EPI_BIAS_ACT, ACT_GELU, 1>(ctx, ta, tb, to, p, s);
             if (e->act == JAT_ACT_SILU && e->out_dtype == JAT_DTYPE_BF16)

@@ -217,8 +217,12 @@ __device__ __forceinline__ void global_to_slab(uint32_t slab_addr, int lane, con
 // MC = CTA pairs per cluster (CG == 2 only).  MC == 2: a cluster of 4 CTAs computes two 256-row M blocks of the same N block;
 // every CTA loads HALF of its pair's share of the W tile and multicasts it to the CTA with the same pair-rank in the other
 // pair, so the cluster reads W once instead of twice (the long-K GEMMs are bound by the L2 -> SM operand stream).
-template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = epilogue warps: 8 (default; two column halves, two staging slabs per warp) or 16 (bf16-output epilogues of 256-wide
+// tiles: four column quarters = ONE 64-column slab per warp and tile, single-buffered -- the slab's TMA store was issued a
+// whole tile ago; 640 threads at <= 102 registers).  The training-mode fc1 / GELU' dgrad epilogues run ~33 instructions per
+// output element and are bound by instruction issue and latency with two epilogue warps per scheduler; four hide it.
+template <int BN, int CG, int EPI, int ACT, int OUT_BF16, int A_MN = 0, int B_MN = 0, int MC = 1, int EW = GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using Cfg = GemmCfg<BN, CG>;
@@ -259,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tmem_full[a], 1);
-            mbar_init(&bar_tmem_empty[a], GEMM_EPI_WARPS * CG);
+            mbar_init(&bar_tmem_empty[a], EW * CG);
         }
         fence_barrier_init();
     }
@@ -379,16 +383,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ------------------------------------------------------------------ epilogue
         const int quad = warp & 3;       // TMEM lane quadrant this warp may access
         const int wg = (warp - 4) >> 2;  // column half
-        constexpr int HALF = BN / 2;
-        uint8_t* my_stage = staging + (warp - 4) * 2 * GEMM_SLAB_BYTES;
+        static_assert(EW == 8 || (EW == 16 && BN == 256 && OUT_BF16 && (EPI == EPI_BIAS_ACT || EPI == EPI_DACT)),
+                      "16 epilogue warps: bf16-output epilogues of 256-wide tiles only");
+        constexpr int HALF = BN / (EW / 4);          // columns of the tile this warp owns (a half, or a quarter with EW = 16)
+        constexpr int SLABS = EW == 8 ? 2 : 1;       // staging slabs per warp
+        uint8_t* my_stage = staging + (warp - 4) * SLABS * GEMM_SLAB_BYTES;
         const uint32_t slab_row[2] = {smem_u32(my_stage) + (uint32_t)lane * 128u,
-                                      smem_u32(my_stage + GEMM_SLAB_BYTES) + (uint32_t)lane * 128u};
+                                      smem_u32(my_stage + (SLABS - 1) * GEMM_SLAB_BYTES) + (uint32_t)lane * 128u};
         int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
         const int num_work = gemm_num_work(p);
         constexpr long long WS_REGION = 32LL * HALF;                         // floats per (part, CTA, warp) region
-        constexpr long long WS_PART_STRIDE = (long long)CG * GEMM_EPI_WARPS * WS_REGION;
+        constexpr long long WS_PART_STRIDE = (long long)CG * EW * WS_REGION;
         for (int work = cluster_id; work < num_work; work += num_clusters) {
             const GemmWork wk = gemm_decode_work(p, work);
             const int tile = wk.tile;
@@ -408,7 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             //      (per tile, CTA, warp slab) goes on to the epilogue, on the in-order sum of all parts
             const float* ws_region = nullptr;
             if (wk.tail >= 0) {
-                const long long slab = ((long long)cta_rank * GEMM_EPI_WARPS + (warp - 4)) * WS_REGION;
+                const long long slab = ((long long)cta_rank * EW + (warp - 4)) * WS_REGION;
                 float* tile_ws = p.tail_ws + (long long)wk.tail * p.tail_splits * WS_PART_STRIDE + slab;
                 float4* dst = reinterpret_cast<float4*>(tile_ws + wk.part * WS_PART_STRIDE) + lane;
 #pragma unroll 1
@@ -428,7 +435,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (lane == 0) {
                     if constexpr (CG == 1) mbar_arrive(&bar_tmem_empty[as]);
                     else mbar_arrive_cluster(&bar_tmem_empty[as], cluster_rank & ~1u);
-                    int* cnt = p.tail_cnt + (wk.tail * CG + (int)cta_rank) * GEMM_EPI_WARPS + (warp - 4);
+                    int* cnt = p.tail_cnt + (wk.tail * CG + (int)cta_rank) * EW + (warp - 4);
                     last = atomicAdd(cnt, 1) == p.tail_splits - 1;
                     if (last) *cnt = 0;  // every part has arrived: reset for the next launch
                 }
@@ -460,7 +467,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
                 for (int sl = 0; sl < HALF / 64; ++sl) {  // slab = 64 bf16 columns
                     const int n0 = n_base + sl * 64;
-                    if (lane == 0) tma_store_wait_read<1>();
+                    if (lane == 0) tma_store_wait_read<SLABS - 1>();
                     __syncwarp();
                     uint32_t uw[32];  // EPI_DACT: the 64 pre-activations of this thread's row, packed bf16 pairs
                     if constexpr (EPI == EPI_DACT) {
@@ -475,13 +482,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             uw[4 * c] = t4.x; uw[4 * c + 1] = t4.y; uw[4 * c + 2] = t4.z; uw[4 * c + 3] = t4.w;
                         }
                     }
-                    uint32_t v[2][32];
-                    load32(sl * 64, v[0]);
-                    load32(sl * 64 + 32, v[1]);
+                    // (the accumulator half is read from tensor memory where it is used -- twice when the pre-activation copy
+                    //  is kept -- instead of holding 64 values across both passes: the 16-warp variant has 96 registers)
                     if constexpr (EPI == EPI_BIAS_ACT) {
                         if (use_aux) {  // pass 1: the pre-activation acc + bias (bf16) through the slab into p.aux
 #pragma unroll
                             for (int hx = 0; hx < 2; ++hx) {
+                                uint32_t v[32];
+                                load32(sl * 64 + hx * 32, v);
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
                                     float f[8];
@@ -489,10 +497,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     for (int q = 0; q < 8; q += 4) {
                                         const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hx * 32 + j + q))
                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                                        f[q + 0] = __uint_as_float(v[hx][j + q + 0]) + b4.x;
-                                        f[q + 1] = __uint_as_float(v[hx][j + q + 1]) + b4.y;
-                                        f[q + 2] = __uint_as_float(v[hx][j + q + 2]) + b4.z;
-                                        f[q + 3] = __uint_as_float(v[hx][j + q + 3]) + b4.w;
+                                        f[q + 0] = __uint_as_float(v[j + q + 0]) + b4.x;
+                                        f[q + 1] = __uint_as_float(v[j + q + 1]) + b4.y;
+                                        f[q + 2] = __uint_as_float(v[j + q + 2]) + b4.z;
+                                        f[q + 3] = __uint_as_float(v[j + q + 3]) + b4.w;
                                     }
                                     st_slab_chunk(slab_row[buf], lane, hx * 4 + j / 8, pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
                                                   pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -505,6 +513,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
 #pragma unroll
                     for (int hx = 0; hx < 2; ++hx) {
+                        uint32_t v[32];
+                        load32(sl * 64 + hx * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             float f[8];
@@ -512,10 +522,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             for (int q = 0; q < 8; q += 4) {
                                 const float4 b4 = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hx * 32 + j + q))
                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                                f[q + 0] = __uint_as_float(v[hx][j + q + 0]) + b4.x;
-                                f[q + 1] = __uint_as_float(v[hx][j + q + 1]) + b4.y;
-                                f[q + 2] = __uint_as_float(v[hx][j + q + 2]) + b4.z;
-                                f[q + 3] = __uint_as_float(v[hx][j + q + 3]) + b4.w;
+                                f[q + 0] = __uint_as_float(v[j + q + 0]) + b4.x;
+                                f[q + 1] = __uint_as_float(v[j + q + 1]) + b4.y;
+                                f[q + 2] = __uint_as_float(v[j + q + 2]) + b4.z;
+                                f[q + 3] = __uint_as_float(v[j + q + 3]) + b4.w;
                             }
                             if constexpr (EPI == EPI_DACT) {
 #pragma unroll
@@ -546,7 +556,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (row0 < p.M) tma_store_2d(&tmap_out, my_stage + buf * GEMM_SLAB_BYTES, n0, row0);
                         tma_store_commit();
                     }
-                    buf ^= 1;
+                    if constexpr (SLABS == 2) buf ^= 1;
                 }
             } else if constexpr (EPI == EPI_BIAS_ACT || EPI == EPI_GATE_RESIDUAL || EPI == EPI_ACCUM) {
                 // f32 slabs of 32 columns.  GATE_RESIDUAL: slab = gate * (acc + bias), TMA-reduce-added into x.

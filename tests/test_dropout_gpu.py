@@ -117,6 +117,36 @@ def test_gemm_bias_act_dropout_and_dgrad(ops, L):
     assert rel_l2(du.float(), uf.grad) < 6e-3
 
 
+@pytest.mark.parametrize("cta_pair,block_n", [(1, 256), (0, 128)])
+def test_training_shape_fc1_and_gelu_dgrad_epilogues(ops, L, cta_pair, block_n):
+    """The training step's fc1 forward (pre-activation copy + dropout) and GELU' dgrad at their real shape (M = 9660 token
+    rows, 1280 -> 5120): 760 tiles on the persistent grid.  With 256-wide CTA-pair tiles these two epilogues run on 16
+    epilogue warps with one single-buffered staging slab per warp (gemm_tcgen05_kernel, EW = 16); (0, 128) is the 8-warp
+    schedule on the same data.  Ragged last row block (9660 = 37 x 256 + 188)."""
+    torch.manual_seed(13)
+    M, K, N, p = 9660, 1280, 5120, 0.1
+    seed = ops.dropout_site_seed(5, 7, L.DROP_SITE_MLP_HIDDEN)
+    A = torch.randn(M, K, device=dev()).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev()) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev())
+    mask = ops.dropout_scale_mask(M, N, p, seed, dev())
+    u = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    got = ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, aux=u, drop_p=p, drop_seed=seed, cta_pair=cta_pair, block_n=block_n)
+    pre = A.float() @ W.float().T + bias
+    assert torch.isfinite(u.float()).all() and rel_l2(u.float(), pre) < 4e-3
+    assert rel_l2(got.float(), torch.nn.functional.gelu(pre) * mask) < 6e-3
+    plain = ops.gemm(A, W, bias=bias, act=L.ACT_GELU_ERF, cta_pair=cta_pair, block_n=block_n)      # 8-warp epilogue, no extras
+    assert torch.equal(got[mask != 0], (plain.float() * mask).to(torch.bfloat16)[mask != 0]) or \
+        rel_l2(got.float(), plain.float() * mask) < 4e-3
+    W2 = (torch.randn(K, N, device=dev()) / math.sqrt(N)).to(torch.bfloat16)   # [out, hidden]
+    dY = torch.randn(M, K, device=dev()).to(torch.bfloat16)
+    du = ops.gemm(dY, W2, kind=L.EPI_DACT, act=L.ACT_GELU_ERF, aux=u, w_transposed=True, drop_p=p, drop_seed=seed,
+                  cta_pair=cta_pair, block_n=block_n)
+    uf = u.float().requires_grad_(True)
+    (torch.nn.functional.gelu(uf) * mask).backward(dY.float() @ W2.float())
+    assert rel_l2(du.float(), uf.grad) < 6e-3
+
+
 @pytest.mark.parametrize("with_path", [False, True])
 def test_gemm_gate_residual_dropout_and_gate_bwd(ops, L, with_path):
     torch.manual_seed(4)
