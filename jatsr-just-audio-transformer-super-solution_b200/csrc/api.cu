@@ -421,7 +421,7 @@ static int dispatch_gemm_mc2(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
                 e->out_dtype);
 }
 
-// 16 epilogue warps (see gemm_tcgen05_kernel) for the bias + GELU epilogue: JAT_GEMM_EW16 selects when -- 0 never, 1 when the
+// 16 epilogue warps (see gemm_tcgen05_kernel) for the bias + GELU and the GELU' dgrad epilogues: JAT_GEMM_EW16 selects when -- 0 never, 1 when the
 // epilogue carries the training extras (pre-activation copy or dropout: ~33 instructions per element; fc1 forward of the
 // training step 135 -> 113 us, class 8.75 -> 8.14 ms per step), 2 always.
 // Not combined with the workspace tail split (its per-warp regions are laid out for 8 warps).
@@ -450,8 +450,11 @@ static int dispatch_gemm_epi(jat_ctx* ctx, const CUtensorMap& ta, const CUtensor
             case JAT_EPI_ACCUM:
                 return launch_gemm<BN, CG, EPI_ACCUM, ACT_NONE, 0, 0, 1>(ctx, ta, tb, to, p, s);
             case JAT_EPI_DACT:
-                // (16 epilogue warps were measured SLOWER for this epilogue: 141.7 vs 132.8 us -- its 64 pre-activation values
-                //  per thread do not fit the 96-register budget next to the accumulator half; it stays on 8 warps)
+                if constexpr (BN == 256 && CG == 2) {
+                    // (GELU' dgrad class 3.90 -> 3.61 ms per training step; pre-activations loaded per 32-column half)
+                    if (e->act == JAT_ACT_GELU_ERF && gemm_ew16(p))
+                        return launch_gemm<256, 2, EPI_DACT, ACT_GELU, 1, 0, 1, 1, 16>(ctx, ta, tb, to, p, s);
+                }
                 if (e->act == JAT_ACT_GELU_ERF) return launch_gemm<BN, CG, EPI_DACT, ACT_GELU, 1, 0, 1>(ctx, ta, tb, to, p, s);
                 if (e->act == JAT_ACT_SILU) return launch_gemm<BN, CG, EPI_DACT, ACT_SILU, 1, 0, 1>(ctx, ta, tb, to, p, s);
                 break;

@@ -469,12 +469,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const int n0 = n_base + sl * 64;
                     if (lane == 0) tma_store_wait_read<SLABS - 1>();
                     __syncwarp();
-                    uint32_t uw[32];  // EPI_DACT: the 64 pre-activations of this thread's row, packed bf16 pairs
-                    if constexpr (EPI == EPI_DACT) {
-                        // (one 16-byte load per thread and chunk, issued ahead of the TMEM read-out: measured faster than
-                        //  staging the rows through the slab with coalesced loads -- the extra shared-memory round trip
-                        //  sits on the epilogue's critical path, 3.99 vs 3.77 ms per training step)
-                        const __nv_bfloat16* aux_row = aux_slab + (long long)lane * p.ld_aux + n0;
+                    // EPI_DACT: the 64 pre-activations of this thread's row (packed bf16 pairs), one 16-byte load per chunk, all
+                    // issued ahead of the TMEM read-out (measured faster than staging the rows through the slab with coalesced
+                    // loads: the extra shared-memory round trip sits on the epilogue's critical path, 3.99 vs 3.77 ms per step).
+                    // With 16 epilogue warps (96 registers) the loads are issued per 32-column half instead.
+                    uint32_t uw[EW == 8 ? 32 : 16];
+                    const __nv_bfloat16* aux_row = aux_slab + (long long)lane * p.ld_aux + n0;
+                    auto load_u = [&](int c0, int nchunks) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c >= nchunks) break;
+                            uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+                            if (use_aux && row_ok) t4 = __ldg(reinterpret_cast<const uint4*>(aux_row) + c0 + c);
+                            uw[4 * c] = t4.x; uw[4 * c + 1] = t4.y; uw[4 * c + 2] = t4.z; uw[4 * c + 3] = t4.w;
+                        }
+                    };
+                    if constexpr (EPI == EPI_DACT && EW == 8) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
@@ -513,6 +523,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
 #pragma unroll
                     for (int hx = 0; hx < 2; ++hx) {
+                        if constexpr (EPI == EPI_DACT && EW != 8) load_u(hx * 4, 4);
                         uint32_t v[32];
                         load32(sl * 64 + hx * 32, v);
 #pragma unroll
@@ -530,7 +541,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if constexpr (EPI == EPI_DACT) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
-                                    const uint32_t w2 = uw[hx * 16 + j / 2 + q];
+                                    const uint32_t w2 = uw[(EW == 8 ? hx * 16 : 0) + j / 2 + q];
                                     f[2 * q] *= dact<ACT>(__uint_as_float(w2 << 16));
                                     f[2 * q + 1] *= dact<ACT>(__uint_as_float(w2 & 0xffff0000u));
                                 }
