@@ -19,7 +19,8 @@ JSON keys beyond the base contract:
   cpu_baseline the torch (ATen) fp32 restatement of the reference timed on the host cores on a bounded sample
   train        (every N) BASELINE configs[3]: the DDP training step, batch 28 per GPU -- ms/step, fraction of the tensor
                roofline, per-class kernel ms, the all-reduce cost that is not hidden, a cross-rank parameter checksum
-  long, v2     (N = 1) BASELINE configs[4] (10-minute track, chunked) and configs[1] (v2 288 M, B = 1, 25 steps)
+  long         (every N) BASELINE configs[4]: the 10-minute track, its 43 chunks dealt over the N GPUs (strong scaling)
+  v2           (N = 1) BASELINE configs[1] (v2 288 M, B = 1, 25 steps)
   gpu_baseline (N = 1) stock PyTorch on the same B200: the torch restatement of the reference (oracle/torch_dit.py) for the
                same denoise step under eager fp32, eager bf16 autocast and torch.compile + bf16 autocast, and for the training
                step under eager bf16 autocast; `speedup_vs_*` = ours / torch on the same GPU
@@ -751,7 +752,7 @@ def main():
     ap.add_argument("--mode", default="sample", choices=["sample", "train", "long", "gpu_baseline"],
                     help="sample = headline CFG denoise step (configs[2]) + the sub-records of --sub; train = only the DDP training "
                          "step (configs[3]); long = only the 10-minute track (configs[4]); gpu_baseline = only stock PyTorch on this GPU")
-    ap.add_argument("--sub", default="auto", help="sub-records added to the headline line: auto (train at every N; long, v2, "
+    ap.add_argument("--sub", default="auto", help="sub-records added to the headline line: auto (train and long at every N; v2, "
                                                   "gpu_baseline at N = 1), none, or a comma list of train,long,v2,gpu_baseline")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
@@ -880,7 +881,7 @@ def main():
                          f"rows, depth 28) took {ts:.2f} s on {threads} threads; scaled x{B // CPU_SAMPLE_B} to the batch-28 step"}
 
     # ---- sub-records: the other BASELINE configs and the stock-PyTorch comparator
-    subs = a.sub.split(",") if a.sub not in ("auto", "none") else (["train"] + (["long", "v2", "gpu_baseline"] if world == 1 else [])
+    subs = a.sub.split(",") if a.sub not in ("auto", "none") else (["train", "long"] + (["v2", "gpu_baseline"] if world == 1 else [])
                                                                     if a.sub == "auto" else [])
     extra = {}
 
