@@ -357,13 +357,16 @@ def train_record(a, K, W, D_, model=None):
             # torch's default 25 MB buckets: the all-reduce of the LAST bucket cannot overlap anything, so it should be small
             bucket_cap_mb=int(os.environ.get("JAT_DDP_BUCKET_MB", "25")),
             gradient_as_bucket_view=os.environ.get("JAT_DDP_BUCKET_VIEW", "1") == "1")
-        if grad_wire == "bf16":   # bf16 payload through two fused library passes (jat_b200.ddp)
-            jat_b200.ddp.register_bf16_allreduce(net)
+        # (registered below, once the optimizer exists: FusedAdamW consumes the bf16 payload directly)
     fused_opt = os.environ.get("JAT_BENCH_TORCH_OPT", "0") == "0"
     if fused_opt:   # clip_grad_norm_(1.0) + AdamW + bf16 re-pack in two multi-tensor passes (jat_b200.FusedAdamW)
         opt = jat_b200.FusedAdamW(model.parameters(), lr=5e-5, weight_decay=0.1, max_grad_norm=1.0, model=model)
     else:           # the reference's own calls, train_ddp_v3mod2.py:709, 926-928
         opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.1, fused=True)
+    if world > 1 and grad_wire == "bf16":   # bf16 payload (jat_b200.ddp): one fused compress pass, consumed by FusedAdamW as is
+        fused_consumer = fused_opt and os.environ.get("JAT_DDP_FUSED_CONSUMER", "1") == "1" and \
+            os.environ.get("JAT_DDP_BUCKET_VIEW", "1") == "1"
+        jat_b200.ddp.register_bf16_allreduce(net, optimizer=opt if fused_consumer else None)
     gd = torch.Generator(device=dev).manual_seed(100 + rank)
     hr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3                   # raw (un-normalised) DAC latents
     lr = torch.randn(B, C, T, generator=gd, device=dev) * 2.0 + 0.3

@@ -353,9 +353,12 @@ int jat_patchify_single(jat_ctx* ctx, const float* x, void* out_bf16, int B, int
  * train_ddp_v3mod2.py:926-928 and the bf16 re-pack of the updated weights; same arithmetic as ATen's fused AdamW) ----
  * One entry per parameter tensor, all f32 and contiguous; the table lives in DEVICE memory.  `packed` (optional) receives
  * the updated values as well, in packed_dtype (JAT_DTYPE_BF16 / JAT_DTYPE_F32): the copy the forward GEMMs read.
- * vec_ok = 1 when every pointer is 16-byte aligned and numel % 4 == 0 (128-bit accesses), else 0 (scalar path).
+ * packed_dtype bit 1 (JAT_ADAMW_GRAD_BF16 = 2) marks `grad` as pointing at bf16 values (the all-reduced payload of the bf16
+ * gradient exchange): the update then consumes the payload directly and the f32 bucket is never re-expanded.
+ * vec_ok = 1 when every pointer is 16-byte aligned (8-byte for a bf16 grad) and numel % 4 == 0 (128-bit accesses), else 0.
  * chunk_first [n_tensors] (device, int32): index of each tensor's first chunk, a chunk being jat_adamw_chunk_elems()
  * consecutive elements (the last chunk of a tensor may be short); total_chunks = their sum. */
+#define JAT_ADAMW_GRAD_BF16 2
 typedef struct jat_adamw_tensor {
     float* param;
     const float* grad;

@@ -24,11 +24,23 @@ struct OptTensor {  // mirrors jat_adamw_tensor (include/jat_b200.h)
     float* exp_avg_sq;
     void* packed;       // optional copy of the updated value in the layout the forward reads (NULL: none)
     long long numel;
-    int packed_dtype;   // JAT_DTYPE_BF16 / JAT_DTYPE_F32
+    int packed_dtype;   // bit 0: dtype of `packed` (JAT_DTYPE_BF16 = 1 / JAT_DTYPE_F32 = 0); bit 1 (JAT_ADAMW_GRAD_BF16): `grad`
+                        // points at bf16 values (the all-reduced payload of the bf16 gradient exchange, jat_b200.ddp)
     int vec_ok;         // every pointer 16-byte aligned and numel % 4 == 0
     float bias_corr1;       // 1 - beta1^step of THIS tensor (parameters may have been frozen for some steps)
     float bias_corr2_sqrt;  // sqrt(1 - beta2^step)
 };
+
+// 4 consecutive gradient elements, f32 or bf16 source
+__device__ __forceinline__ float4 opt_load_grad4(const float* g, long long q, bool bf16) {
+    if (!bf16) return __ldcs(reinterpret_cast<const float4*>(g) + q);
+    const uint2 w = __ldcs(reinterpret_cast<const uint2*>(g) + q);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+__device__ __forceinline__ float opt_load_grad1(const float* g, long long i, bool bf16) {
+    return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]) : g[i];
+}
 
 __device__ __forceinline__ int opt_find_tensor(const int* __restrict__ chunk_first, int n_tensors, int chunk) {
     int lo = 0, hi = n_tensors - 1;  // largest i with chunk_first[i] <= chunk
@@ -48,20 +60,21 @@ grad_sumsq_kernel(const OptTensor* __restrict__ table, const int* __restrict__ c
     const OptTensor t = table[ti];
     const long long e0 = (long long)(chunk - __ldg(chunk_first + ti)) * OPT_CHUNK;
     const long long n = t.numel - e0 < OPT_CHUNK ? t.numel - e0 : OPT_CHUNK;
-    const float* g = t.grad + e0;
+    const bool gbf = (t.packed_dtype & 2) != 0;
+    const float* g = gbf ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(t.grad) + e0) : t.grad + e0;
     float acc = 0.f;
     if (t.vec_ok) {
         float4 v[OPT_CHUNK / 4 / OPT_THREADS];
 #pragma unroll
         for (int i = 0; i < OPT_CHUNK / 4 / OPT_THREADS; ++i) {
             const int q = i * OPT_THREADS + threadIdx.x;
-            v[i] = q * 4 < n ? __ldcs(reinterpret_cast<const float4*>(g) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = q * 4 < n ? opt_load_grad4(g, q, gbf) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < OPT_CHUNK / 4 / OPT_THREADS; ++i)
             acc += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     } else {
-        for (long long i = threadIdx.x; i < n; i += OPT_THREADS) { const float x = g[i]; acc += x * x; }
+        for (long long i = threadIdx.x; i < n; i += OPT_THREADS) { const float x = opt_load_grad1(g, i, gbf); acc += x * x; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -140,17 +153,19 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
         clip = c < 1.0f ? c : 1.0f;
     }
     const float step_size = (float)(a.lr / (double)t.bias_corr1);
+    const bool gbf = (t.packed_dtype & 2) != 0;
+    const int pdt = t.packed_dtype & 1;
+    const float* gsrc = gbf ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(t.grad) + e0) : t.grad + e0;
     if (t.vec_ok) {
         constexpr int NV = OPT_CHUNK / 4 / OPT_THREADS;
         float4* p4 = reinterpret_cast<float4*>(t.param + e0);
-        const float4* g4 = reinterpret_cast<const float4*>(t.grad + e0);
         float4* m4 = reinterpret_cast<float4*>(t.exp_avg + e0);
         float4* v4 = reinterpret_cast<float4*>(t.exp_avg_sq + e0);
         float4 p[NV], g[NV], m[NV], v[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int q = i * OPT_THREADS + threadIdx.x;
-            if (q * 4 < n) { p[i] = __ldcs(p4 + q); g[i] = __ldcs(g4 + q); m[i] = __ldcs(m4 + q); v[i] = __ldcs(v4 + q); }
+            if (q * 4 < n) { p[i] = __ldcs(p4 + q); g[i] = opt_load_grad4(gsrc, q, gbf); m[i] = __ldcs(m4 + q); v[i] = __ldcs(v4 + q); }
         }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -162,7 +177,7 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
             adamw_one<F64>(p[i].w, g[i].w, m[i].w, v[i].w, a, clip, step_size, t.bias_corr2_sqrt);
             __stcs(p4 + q, p[i]); __stcs(m4 + q, m[i]); __stcs(v4 + q, v[i]);
             if (t.packed != nullptr) {
-                if (t.packed_dtype == 1)   // JAT_DTYPE_BF16: stays in L2 for the next forward where it fits
+                if (pdt == 1)   // JAT_DTYPE_BF16: stays in L2 for the next forward where it fits
                     reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.packed) + e0)[q] =
                         make_uint2(pack_bf16(p[i].x, p[i].y), pack_bf16(p[i].z, p[i].w));
                 else
@@ -172,10 +187,10 @@ adamw_kernel(const OptTensor* __restrict__ table, const int* __restrict__ chunk_
     } else {
         for (long long i = threadIdx.x; i < n; i += OPT_THREADS) {
             float p = t.param[e0 + i], m = t.exp_avg[e0 + i], v = t.exp_avg_sq[e0 + i];
-            adamw_one<F64>(p, t.grad[e0 + i], m, v, a, clip, step_size, t.bias_corr2_sqrt);
+            adamw_one<F64>(p, opt_load_grad1(gsrc, i, gbf), m, v, a, clip, step_size, t.bias_corr2_sqrt);
             t.param[e0 + i] = p; t.exp_avg[e0 + i] = m; t.exp_avg_sq[e0 + i] = v;
             if (t.packed != nullptr) {
-                if (t.packed_dtype == 1) reinterpret_cast<__nv_bfloat16*>(t.packed)[e0 + i] = __float2bfloat16_rn(p);
+                if (pdt == 1) reinterpret_cast<__nv_bfloat16*>(t.packed)[e0 + i] = __float2bfloat16_rn(p);
                 else reinterpret_cast<float*>(t.packed)[e0 + i] = p;
             }
         }

@@ -16,6 +16,11 @@ torch ships a `bf16_compress_hook` with the same dataflow built from `Tensor.to`
 two allocations per bucket); at 8 GPUs it was SLOWER than the plain f32 all-reduce.  The two fused passes
 here cost 12 B per parameter per step in total.
 
+With `optimizer=` a `jat_b200.FusedAdamW`, step 3 is dropped as well ("fused consumer"): the update and the gradient-norm pass
+read the all-reduced bf16 payload directly (`JAT_ADAMW_GRAD_BF16` table entries), the f32 buckets are never re-expanded and
+`.grad` keeps the rank's LOCAL f32 gradient -- so this mode is for loops whose only consumer of the gradients is that
+optimizer (its `max_grad_norm` clipping included); anything else that reads `.grad` should use the default mode.
+
 Numerics: each rank's gradient is rounded once to bf16 (relative 2^-9) before the sum and the sum once more: the exchanged
 gradient differs from the f32 all-reduce by rel-L2 ~3e-3 (tests/_ddp_worker.py asserts < 5e-3; all ranks hold bit-identical
 results, so parameters stay in lock-step).  Keep the default f32 exchange when that matters more than step time.
@@ -29,10 +34,13 @@ from .ops import _ctx, _stream
 
 
 class Bf16AllreduceState:
-    def __init__(self, process_group=None):
+    def __init__(self, process_group=None, optimizer=None):
         self.group = process_group if process_group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.payload = {}   # bucket index -> persistent bf16 buffer
+        self.optimizer = optimizer   # FusedAdamW consuming the payload directly (fused consumer), or None
+        self.where = {}     # id(parameter) -> (payload buffer, element offset): where its reduced bf16 gradient lives
+        self.layout = {}    # bucket index -> (buffer data_ptr, numel) the mapping above was built for
         # gloo (CPU-tested path / single-GPU boxes) has no bf16 reduction: the bf16-rounded values travel as f32 there
         self.wire_f32 = dist.get_backend(self.group) != "nccl"
 
@@ -55,6 +63,23 @@ def bf16_allreduce_hook(state: Bf16AllreduceState, bucket: dist.GradBucket):
     wire = pay.float() if state.wire_f32 else pay
     fut = dist.all_reduce(wire, group=state.group, async_op=True).get_future()
 
+    if state.optimizer is not None:
+        # fused consumer: remember where each parameter's reduced gradient sits in the payload (DDP rebuilds its buckets once,
+        # after the first backward pass), leave the f32 bucket alone
+        key = (grads.data_ptr(), n, pay.data_ptr())
+        if state.layout.get(bucket.index()) != key:
+            base = grads.data_ptr()
+            for p_, g_ in zip(bucket.parameters(), bucket.gradients()):
+                state.where[id(p_)] = (pay, (g_.data_ptr() - base) // 4)
+            state.layout[bucket.index()] = key
+            state.optimizer._groups = None     # rebuild the pointer table at the next step
+
+        def keep(f):
+            if state.wire_f32:
+                pay.copy_(f.value()[0])
+            return grads
+        return fut.then(keep)
+
     def expand(f):
         if state.wire_f32:
             pay.copy_(f.value()[0])
@@ -64,8 +89,16 @@ def bf16_allreduce_hook(state: Bf16AllreduceState, bucket: dist.GradBucket):
     return fut.then(expand)
 
 
-def register_bf16_allreduce(ddp_model, process_group=None):
-    """Install the bf16 gradient exchange on a `DistributedDataParallel` instance; returns the hook state."""
-    state = Bf16AllreduceState(process_group)
+def register_bf16_allreduce(ddp_model, process_group=None, optimizer=None):
+    """Install the bf16 gradient exchange on a `DistributedDataParallel` instance; returns the hook state.
+    optimizer: a `jat_b200.FusedAdamW` that will consume the reduced bf16 payload directly (see the module docstring);
+    needs `gradient_as_bucket_view=True` (the parameter -> payload map is read off the bucket views)."""
+    state = Bf16AllreduceState(process_group, optimizer)
+    if optimizer is not None:
+        if not hasattr(optimizer, "_grad_source"):
+            raise L.JatError(L.ERR_BAD_ARG, "register_bf16_allreduce(optimizer=...) needs a jat_b200.FusedAdamW")
+        if not getattr(ddp_model, "gradient_as_bucket_view", False):
+            raise L.JatError(L.ERR_BAD_ARG, "the fused consumer needs DistributedDataParallel(..., gradient_as_bucket_view=True)")
+        optimizer._grad_source = state
     ddp_model.register_comm_hook(state, bf16_allreduce_hook)
     return state

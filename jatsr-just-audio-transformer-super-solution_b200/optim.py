@@ -21,8 +21,12 @@ from .ops import _stream
 class _Group:
     """Device table (jat_adamw_tensor [n]) + chunk index of one parameter group."""
 
-    def __init__(self, params, states, packed_of, device):
+    def __init__(self, params, states, packed_of, device, grad_source=None):
         self.params = params
+        # reduced bf16 gradients living in the payload buffers of the bf16 gradient exchange (jat_b200.ddp, fused consumer):
+        # (payload tensor, element offset) per parameter, or None -> the parameter's f32 .grad
+        where = grad_source.where if grad_source is not None else {}
+        self.bf16_src = [where.get(id(p)) for p in params]
         self.ids = [id(p) for p in params]
         n = len(params)
         chunk = L.load().jat_adamw_chunk_elems()
@@ -41,6 +45,8 @@ class _Group:
         self.static_ok = torch.tensor([all(r[j] % 16 == 0 for j in (0, 2, 3, 4)) and r[5] % 4 == 0 for r in rows])
         self.dtype_bits = torch.tensor([1 if (d is not None and d.dtype == torch.bfloat16) else 0 for d in dsts],
                                        dtype=torch.int64)
+        self.grad_bits = torch.tensor([0 if w is None else 2 for w in self.bf16_src], dtype=torch.int64)    # JAT_ADAMW_GRAD_BF16
+        self.grad_align = torch.tensor([16 if w is None else 8 for w in self.bf16_src], dtype=torch.int64)
         self.key = self._key(states)
         # every tensor at the same step count (the usual case): kept as one python int, see upload()
         st = [float(states[p]["step"]) for p in params]
@@ -59,7 +65,8 @@ class _Group:
         matters here: under DDP the host is NOT ahead of the GPU at the end of the backward, so every 100 us spent before the
         update kernels are launched is a stall of the device.  The common case (every tensor at the same step) therefore
         avoids the per-tensor work: one python-side step count, two scalars broadcast into the table."""
-        g = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
+        g = torch.tensor([p.grad.data_ptr() if w is None else w[0].data_ptr() + 2 * w[1] for p, w in zip(self.params, self.bf16_src)],
+                         dtype=torch.int64)
         k = self.turn
         self.turn ^= 1
         if self.done[k] is not None:
@@ -67,7 +74,7 @@ class _Group:
         h = self.host[k]
         h.copy_(self.static)
         h[:, 1] = g
-        h[:, 6] = self.dtype_bits | ((self.static_ok & (g % 16 == 0)).to(torch.int64) << 32)
+        h[:, 6] = self.dtype_bits | self.grad_bits | ((self.static_ok & (g % self.grad_align == 0)).to(torch.int64) << 32)
         if self.uniform_step is not None:
             self.uniform_step += 1
             st = float(self.uniform_step)
@@ -100,6 +107,7 @@ class FusedAdamW(torch.optim.AdamW):
         self._packed_seen = None
         self._sumsq = None
         self._covers_model = False
+        self._grad_source = None   # set by jat_b200.ddp.register_bf16_allreduce(..., optimizer=self)
         self.grad_norm = None
 
     # state in torch.optim.AdamW's layout (torch/optim/adam.py:_init_group): step (f32 scalar), exp_avg, exp_avg_sq
@@ -133,7 +141,7 @@ class FusedAdamW(torch.optim.AdamW):
                 if self.state[p]["exp_avg"].device != device:  # state loaded from a checkpoint on another device
                     for k in ("exp_avg", "exp_avg_sq"):
                         self.state[p][k] = self.state[p][k].to(device)
-            self._groups.append(_Group(params, self.state, packed_of, device) if params else None)
+            self._groups.append(_Group(params, self.state, packed_of, device, self._grad_source) if params else None)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=device)
         # the packed copies may be declared fresh after a step only if this optimizer updates every parameter they mirror
         mine = {id(p) for g in self._groups if g is not None for p in g.params}

@@ -24,7 +24,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("mode,cls", [("reference", "JaT_AudioSR_V2"), ("view", "JaT_AudioSR_V2"), ("view", "JaT_AudioSR_V3"),
-                                      ("view_bf16", "JaT_AudioSR_V2")])
+                                      ("view_bf16", "JaT_AudioSR_V2"),
+                                      ("view_bf16_fused", "JaT_AudioSR_V3")])
 def test_two_rank_ddp_matches_single_process(mode, cls):
     env = dict(os.environ, OMP_NUM_THREADS="4")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
