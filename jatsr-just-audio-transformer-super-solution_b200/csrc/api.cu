@@ -887,8 +887,32 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
             adaln_gate_bwd_kernel<NORM, GATE, 512><<<grid, block, 0, s>>>(dh, x, rsp, scale, mod_batch_stride, weight, dx, dshift, \
                 dscale, dmod_batch_stride, dweight, y, gate, dy, dgate, xs, drop, gate_rowscale, D, tokens_per_batch, rows); \
     } while (0)
-    if (norm_kind == JAT_NORM_LAYERNORM) { if (has_gate) JAT_AGB(0, 1); else JAT_AGB(0, 0); }
-    else { if (has_gate) JAT_AGB(1, 1); else JAT_AGB(1, 0); }
+    // staged form (inputs through shared memory by the bulk-copy engine) whenever the rows are 16-byte granular
+    static const int staged_env = [] { const char* v = getenv("JAT_AGB_STAGED"); return v ? atoi(v) : 1; }();
+    const size_t stage_smem = (size_t)AGS_STAGES * AGS_ROWS * D * (has_gate ? 12 : 10);
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                             reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const bool staged = staged_env != 0 && D % 8 == 0 && aligned16 && stage_smem <= (block.x <= 320 ? 110u : 220u) * 1024u;
+#define JAT_AGS(NORM, GATE, T)                                                                                           \
+    do {                                                                                                                 \
+        auto kern = adaln_gate_bwd_staged_kernel<NORM, GATE, T>;                                                         \
+        JAT_TRY(ensure_dyn_smem(ctx, (const void*)kern, (T <= 320 ? 110 : 220) * 1024));                                 \
+        int rows2 = (tokens_per_batch + per_batch - 1) / per_batch;                                                      \
+        rows2 = (rows2 + AGS_ROWS - 1) / AGS_ROWS * AGS_ROWS;                                                            \
+        dim3 grid2((tokens_per_batch + rows2 - 1) / rows2, B);                                                           \
+        kern<<<grid2, block, stage_smem, s>>>(dh, x, rsp, scale, mod_batch_stride, weight, dx, dshift, dscale,           \
+            dmod_batch_stride, dweight, y, gate, dy, dgate, xs, drop, gate_rowscale, D, tokens_per_batch, rows2);        \
+    } while (0)
+#define JAT_AGX(NORM, GATE)                                                                                              \
+    do {                                                                                                                 \
+        if (!staged) JAT_AGB(NORM, GATE);                                                                                \
+        else if (block.x <= 320) JAT_AGS(NORM, GATE, 320);                                                               \
+        else JAT_AGS(NORM, GATE, 512);                                                                                   \
+    } while (0)
+    if (norm_kind == JAT_NORM_LAYERNORM) { if (has_gate) JAT_AGX(0, 1); else JAT_AGX(0, 0); }
+    else { if (has_gate) JAT_AGX(1, 1); else JAT_AGX(1, 0); }
+#undef JAT_AGX
+#undef JAT_AGS
 #undef JAT_AGB
     return post_launch(ctx, "adaln_gate_bwd");
 }

@@ -364,6 +364,177 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same kernel with its four input streams (x, dx, dh, y) staged through shared memory by the bulk-copy engine.  The
+// register version above alternates between a load phase and a reduce / write phase (one __syncthreads per row group), so
+// its loads are in flight only part of the time: 46 % of the HBM peak with the issue slots 52 % busy.  Here thread 0 keeps
+// AGS_STAGES groups of AGS_ROWS rows in flight (one bulk copy per stream and group: the rows of a CTA are contiguous), the
+// column threads read a landed stage into registers, and the stage is refilled right after the group's __syncthreads.
+// Stage = AGS_ROWS x D x (4 + 4 + 2 [+ 2]) bytes; 3 stages of 2 rows at D = 1280: 90 KB, two CTAs per SM.
+// Needs D % 8 == 0 and 16-byte aligned bases (the launcher falls back to the register version otherwise).
+// ------------------------------------------------------------------------------------------------
+constexpr int AGS_ROWS = 2;
+constexpr int AGS_STAGES = 3;
+
+template <int NORM_KIND, int HAS_GATE, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 320 ? 2 : 1)
+adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float2* __restrict__ rowstats,
+                             const float* __restrict__ scale, long long mod_bstride, const float* __restrict__ weight,
+                             float* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_bstride,
+                             float* __restrict__ dweight, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+                             __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dbias, DropCfg drop,
+                             const float* __restrict__ rowscale, int D, int tokens_per_batch, int rows_per_cta) {
+    constexpr int R = AGS_ROWS, S = AGS_STAGES;
+    extern __shared__ __align__(128) uint8_t ags_smem[];
+    __shared__ uint64_t full[S];
+    __shared__ float4 red[2][16];  // [buffer][warp] = (sum g, sum g xhat) of the R = 2 rows of a group
+    const int c4 = threadIdx.x, lane = c4 & 31, warp = c4 >> 5, nw = (int)(blockDim.x >> 5);
+    const bool act = c4 < (D >> 2);
+    const int b = (int)(gridDim.y - 1 - blockIdx.y);  // last rows first, as above
+    const float inv_d = 1.0f / (float)D;
+    const uint32_t off_dx = (uint32_t)(R * D) * 4u, off_dh = off_dx * 2u, off_y = off_dh + (uint32_t)(R * D) * 2u;
+    const uint32_t stage_bytes = (uint32_t)(R * D) * (HAS_GATE ? 12u : 10u);
+    const int n0 = (int)(gridDim.x - 1 - blockIdx.x) * rows_per_cta;
+    const int n1 = min(n0 + rows_per_cta, tokens_per_batch);
+    const long long row0 = (long long)b * tokens_per_batch;
+    const int groups = (n1 - n0 + R - 1) / R;
+
+    auto issue = [&](int g) {  // thread 0: the four streams of group g -> stage g % S
+        uint8_t* st = ags_smem + (size_t)(g % S) * stage_bytes;
+        const int rows = min(R, n1 - (n0 + g * R));
+        const long long e0 = (row0 + n0 + g * R) * D;
+        const uint32_t bx = (uint32_t)(rows * D) * 4u, bh = (uint32_t)(rows * D) * 2u;
+        mbar_expect_tx(&full[g % S], 2u * bx + (HAS_GATE ? 2u : 1u) * bh);
+        bulk_load_1d(st, x + e0, bx, &full[g % S]);
+        bulk_load_1d(st + off_dx, dx + e0, bx, &full[g % S]);
+        bulk_load_1d(st + off_dh, dh + e0, bh, &full[g % S]);
+        if (HAS_GATE) bulk_load_1d(st + off_y, y + e0, bh, &full[g % S]);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+        for (int g = 0; g < S && g < groups; ++g) issue(g);
+    }
+    float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), w4 = sc4, g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rs = 1.0f;
+    if (act) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * mod_bstride) + c4);
+        sc4 = make_float4(1.0f + t.x, 1.0f + t.y, 1.0f + t.z, 1.0f + t.w);
+        if (NORM_KIND == 1) w4 = __ldg(reinterpret_cast<const float4*>(weight) + c4);
+        if (HAS_GATE) {
+            rs = rowscale != nullptr ? __ldg(rowscale + b) : 1.0f;
+            g4 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * mod_bstride) + c4);
+            g4.x *= rs; g4.y *= rs; g4.z *= rs; g4.w *= rs;
+        }
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a_shift = zero4, a_scale = zero4, a_w = zero4, a_gate = zero4, a_sum = zero4;
+    float2 st_next[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) st_next[r] = n0 + r < n1 ? __ldg(rowstats + row0 + n0 + r) : make_float2(0.f, 0.f);
+    __syncthreads();  // barrier initialisation visible before anybody waits
+    int buf = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int n = n0 + g * R;
+        float2 stt[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            stt[r] = st_next[r];
+            st_next[r] = n + R + r < n1 ? __ldg(rowstats + row0 + n + R + r) : make_float2(0.f, 0.f);
+        }
+        mbar_wait(&full[g % S], (uint32_t)((g / S) & 1));
+        const uint8_t* st = ags_smem + (size_t)(g % S) * stage_bytes;
+        float4 xv[R], gv[R], ov[R];
+        uint2 yv[R];
+        float sg[R], sgx[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = act && n + r < n1;
+            const float4 xr = ok ? reinterpret_cast<const float4*>(st + (size_t)r * D * 4)[c4] : zero4;
+            ov[r] = ok ? reinterpret_cast<const float4*>(st + off_dx + (size_t)r * D * 4)[c4] : zero4;
+            const float4 d = ok ? bf16x4_to_f32(reinterpret_cast<const uint2*>(st + off_dh + (size_t)r * D * 2)[c4]) : zero4;
+            if (HAS_GATE) yv[r] = ok ? reinterpret_cast<const uint2*>(st + off_y + (size_t)r * D * 2)[c4] : make_uint2(0u, 0u);
+            const float mean = stt[r].x, rstd = stt[r].y;
+            const float4 xh = ok ? make_float4((xr.x - mean) * rstd, (xr.y - mean) * rstd, (xr.z - mean) * rstd, (xr.w - mean) * rstd) : zero4;
+            xv[r] = xh;
+            a_shift.x += d.x; a_shift.y += d.y; a_shift.z += d.z; a_shift.w += d.w;
+            a_scale.x += d.x * xh.x * w4.x; a_scale.y += d.y * xh.y * w4.y; a_scale.z += d.z * xh.z * w4.z; a_scale.w += d.w * xh.w * w4.w;
+            float4 gg = make_float4(d.x * sc4.x, d.y * sc4.y, d.z * sc4.z, d.w * sc4.w);
+            if (NORM_KIND == 1) {
+                a_w.x += gg.x * xh.x; a_w.y += gg.y * xh.y; a_w.z += gg.z * xh.z; a_w.w += gg.w * xh.w;
+                gg.x *= w4.x; gg.y *= w4.y; gg.z *= w4.z; gg.w *= w4.w;
+            }
+            gv[r] = gg;
+            sg[r] = (gg.x + gg.y) + (gg.z + gg.w);
+            sgx[r] = (gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (NORM_KIND == 0) sg[r] += __shfl_xor_sync(0xffffffffu, sg[r], o);
+                sgx[r] += __shfl_xor_sync(0xffffffffu, sgx[r], o);
+            }
+        }
+        if (lane == 0) red[buf][warp] = make_float4(sg[0], sgx[0], sg[1], sgx[1]);
+        __syncthreads();  // every thread holds its part of the stage in registers: the stage can be refilled
+        if (threadIdx.x == 0 && g + S < groups) issue(g + S);
+        float4 tot = zero4;
+        for (int w = 0; w < nw; ++w) {
+            const float4 p0 = red[buf][w];
+            tot.x += p0.x; tot.y += p0.y; tot.z += p0.z; tot.w += p0.w;
+        }
+        buf ^= 1;
+        const float mgs[R] = {tot.x * inv_d, tot.z * inv_d};
+        const float mgxs[R] = {tot.y * inv_d, tot.w * inv_d};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!(act && n + r < n1)) continue;
+            const long long row = row0 + n + r;
+            const float mg = NORM_KIND == 0 ? mgs[r] : 0.0f, mgx = mgxs[r], rd = stt[r].y;
+            float4 o;
+            o.x = rd * (gv[r].x - mg - xv[r].x * mgx) + ov[r].x;
+            o.y = rd * (gv[r].y - mg - xv[r].y * mgx) + ov[r].y;
+            o.z = rd * (gv[r].z - mg - xv[r].z * mgx) + ov[r].z;
+            o.w = rd * (gv[r].w - mg - xv[r].w * mgx) + ov[r].w;
+            reinterpret_cast<float4*>(dx + row * D)[c4] = o;
+            if (HAS_GATE) {
+                const float4 yf = bf16x4_to_f32(yv[r]);
+                a_gate.x += o.x * yf.x; a_gate.y += o.y * yf.y; a_gate.z += o.z * yf.z; a_gate.w += o.w * yf.w;
+                float4 dm = o;
+                if (drop.thresh != 0u) {
+                    const uint32_t rr = (uint32_t)row, cc = (uint32_t)(c4 * 4);
+                    float m0, m1, m2, m3;
+                    drop_scale2(drop, rr, cc, m0, m1);
+                    drop_scale2(drop, rr, cc + 2, m2, m3);
+                    dm.x *= m0; dm.y *= m1; dm.z *= m2; dm.w *= m3;
+                }
+                a_sum.x += dm.x; a_sum.y += dm.y; a_sum.z += dm.z; a_sum.w += dm.w;
+                reinterpret_cast<uint2*>(dy + row * D)[c4] =
+                    make_uint2(pack_bf16(dm.x * g4.x, dm.y * g4.y), pack_bf16(dm.z * g4.z, dm.w * g4.w));
+            }
+        }
+    }
+    if (!act) return;
+    float* p1 = dshift + (long long)b * dmod_bstride + c4 * 4;
+    float* p2 = dscale + (long long)b * dmod_bstride + c4 * 4;
+    atomicAdd(p1, a_shift.x); atomicAdd(p1 + 1, a_shift.y); atomicAdd(p1 + 2, a_shift.z); atomicAdd(p1 + 3, a_shift.w);
+    atomicAdd(p2, a_scale.x); atomicAdd(p2 + 1, a_scale.y); atomicAdd(p2 + 2, a_scale.z); atomicAdd(p2 + 3, a_scale.w);
+    if (NORM_KIND == 1 && dweight != nullptr) {
+        float* p3 = dweight + c4 * 4;
+        atomicAdd(p3, a_w.x); atomicAdd(p3 + 1, a_w.y); atomicAdd(p3 + 2, a_w.z); atomicAdd(p3 + 3, a_w.w);
+    }
+    if (HAS_GATE) {
+        float* dg = dgate + (long long)b * dmod_bstride + c4 * 4;
+        atomicAdd(dg, a_gate.x * rs); atomicAdd(dg + 1, a_gate.y * rs); atomicAdd(dg + 2, a_gate.z * rs); atomicAdd(dg + 3, a_gate.w * rs);
+        if (dbias != nullptr) {
+            float* ds = dbias + c4 * 4;
+            atomicAdd(ds, a_sum.x * g4.x); atomicAdd(ds + 1, a_sum.y * g4.y); atomicAdd(ds + 2, a_sum.z * g4.z); atomicAdd(ds + 3, a_sum.w * g4.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix: out[c] += sum_m a[m, c]   (bias gradients of mlp.0, patch_embed, final_layer, ...).
 // grid = (ceil(cols / 512), row chunks); thread = 4 adjacent columns (8-byte loads), rows strided by the chunk count,
 // 8 loads in flight per thread.

@@ -125,6 +125,14 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const void* tmap, uint6
     else tma_load_2d_2sm(dst, tmap, bar, c0, c1);
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` (multiple of 16, both addresses 16-byte aligned) land at `dst` and
+// are counted on `bar` of this CTA.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // 2D tile store smem -> global (bulk async-group completion). Out-of-bounds rows/cols are clipped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

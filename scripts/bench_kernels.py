@@ -116,6 +116,15 @@ def bench_bwd(iters):
     med, mn = timeit(fn, iters)
     report("adaln_bwd_layernorm", med, mn, bytes_=M * D * 14.0)
     y, dy = bf(M, D), torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    rowstats = torch.stack([x.mean(-1), torch.rsqrt(x.var(-1, unbiased=False) + 1e-6)], -1).contiguous()
+    dbias = torch.zeros(D, device=dev)
+    for name, kw in (("adaln_gate_bwd_nogate", {}),
+                     ("adaln_gate_bwd_gate_drop", dict(y=y, gate=mod[:, 2 * D:3 * D], dgate=dmod[0, :, 2 * D:3 * D], dbias=dbias,
+                                                       drop_p=0.1, drop_seed=5, dy=dy))):
+        fn = lambda: ops.adaln_gate_bwd(dh, x, rowstats, B, Ntok, dx, scale=mod[:, D:2 * D], mod_batch_stride=mod.stride(0),
+                                        dshift=dmod[0, :, :D], dscale=dmod[0, :, D:2 * D], dmod_batch_stride=6 * D, **kw)
+        med, mn = timeit(fn, iters)
+        report(name, med, mn, bytes_=M * D * (18.0 if kw else 14.0))
     fn = lambda: ops.gate_bwd(dx, y, mod[:, 2 * D:3 * D], B, Ntok, dmod[0, :, 2 * D:3 * D], mod_batch_stride=mod.stride(0),
                               dmod_batch_stride=6 * D, dy=dy)
     med, mn = timeit(fn, iters)

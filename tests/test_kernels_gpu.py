@@ -589,7 +589,9 @@ def test_gate_bwd_matches_autograd(ops, with_bias):
 
 
 @pytest.mark.parametrize("norm_kind", [0, 1])
-@pytest.mark.parametrize("D,B,Ntok", [(1280, 28, 345), (1280, 3, 77), (128, 4, 22), (1000, 2, 5)])
+# D % 8 == 0: the shared-memory staged kernel; D = 1004: the register version (rows not 16-byte granular in bf16)
+@pytest.mark.parametrize("D,B,Ntok", [(1280, 28, 345), (1280, 3, 77), (128, 4, 22), (1000, 2, 5), (1004, 2, 9), (2048, 2, 40),
+                                      (1280, 300, 7)])
 @pytest.mark.parametrize("gate_mode", ["none", "gate", "gate_bias_drop"])
 def test_adaln_gate_bwd_fused_matches_autograd(ops, L, norm_kind, D, B, Ntok, gate_mode):
     """Fused norm + modulate backward (+ the gate backward of the branch below, on the updated dx row) against torch
