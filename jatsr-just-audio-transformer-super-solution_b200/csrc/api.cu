@@ -10,7 +10,9 @@
 
 #include <atomic>
 #include <map>
+#include <functional>
 #include <new>
+#include <queue>
 #include <set>
 #include <vector>
 
@@ -56,6 +58,7 @@ struct jat_ctx {
     // the co-resident cluster limit of the 4-CTA multicast GEMM instantiations there
     std::set<const void*> smem_configured;
     std::map<const void*, int> max_clusters;
+    std::map<long long, int> attn_gs;   // (KV-group tiles, G) -> query heads per attention CTA
 };
 static const size_t kTailWsBytesPerSM = 128 * 256 * sizeof(float);
 
@@ -889,7 +892,7 @@ extern "C" int jat_adaln_gate_bwd(jat_ctx* ctx, const void* dh_bf16, const float
     } while (0)
     // staged form (inputs through shared memory by the bulk-copy engine) whenever the rows are 16-byte granular
     static const int staged_env = [] { const char* v = getenv("JAT_AGB_STAGED"); return v ? atoi(v) : 1; }();
-    const size_t stage_smem = (size_t)AGS_STAGES * AGS_ROWS * D * (has_gate ? 12 : 10);
+    const size_t stage_smem = (size_t)AGS_STAGES * AGS_ROWS * D * (has_gate ? 12 : 10) + AGS_PAD;
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
                              reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     const bool staged = staged_env != 0 && D % 8 == 0 && aligned16 && stage_smem <= (block.x <= 320 ? 110u : 220u) * 1024u;
@@ -923,7 +926,9 @@ extern "C" int jat_colsum_bf16(jat_ctx* ctx, const void* a_bf16, int64_t lda, in
     if (M <= 0 || cols <= 0 || cols % 4 != 0 || lda % 4 != 0 || (reinterpret_cast<uintptr_t>(a_bf16) & 7) != 0)
         return fail(JAT_ERR_BAD_SHAPE, "jat_colsum_bf16: need cols %% 4 == 0, lda %% 4 == 0, 8-byte aligned input");
     int chunks = (M + 31) / 32;
-    const int cap = (ctx->sm_count * 16) / ((cols + 511) / 512) + 1;
+    // one wave: 16 CTAs of 128 threads per SM; a grid two CTAs over it (the former "+ 1") ran a second wave for them
+    int cap = (ctx->sm_count * 16) / ((cols + 511) / 512);
+    if (cap < 1) cap = 1;
     if (chunks > cap) chunks = cap;
     dim3 grid((cols + 511) / 512, chunks);
     pre_launch(ctx, TAG_COLSUM, (cudaStream_t)stream);
@@ -1126,6 +1131,40 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, f
     return jat_gqa_attention_fwd_dropout(ctx, qkv, out, lse, B, N, Hq, Hkv, head_dim, 0.0f, 0u, stream);
 }
 
+// Query heads per CTA.  A CTA serves Gs heads of one (query tile, KV group) after staging the group's K / V once; the
+// launch is `groups` x ceil(G / Gs) CTAs, one per SM at a time (512 TMEM columns), handed out full parts first.  Whole
+// groups (Gs = G) stage K / V least often, but 336 CTAs of 5 heads on 148 SMs (training, B = 28) take 3 rounds for 2.27
+// rounds of work; parts of 3 + 2 heads finish in 12.9 head-times instead of 15.  Pick the Gs with the shortest list-schedule
+// makespan, a CTA costing (heads + 0.4) head-times (0.4: barrier / TMEM set-up and the K / V + first Q load before the first MMA).
+static int attention_heads_per_cta(jat_ctx* ctx, long long groups, int G) {
+    const long long key = groups * 64 + G;
+    auto it = ctx->attn_gs.find(key);
+    if (it != ctx->attn_gs.end()) return it->second;
+    const int sms = ctx->sm_count;
+    const double setup = 0.4;
+    int best = G;
+    double best_t = -1.0;
+    for (int gs = G; gs >= 1; --gs) {
+        const int parts = (G + gs - 1) / gs, last = G - (parts - 1) * gs;
+        // list scheduling: CTAs in launch order (full parts first) to the SM that frees up first
+        std::priority_queue<double, std::vector<double>, std::greater<double>> pq;
+        for (int i = 0; i < sms; ++i) pq.push(0.0);
+        double makespan = 0.0;
+        const long long n_full = groups * (parts - 1), n_last = groups;
+        if (n_full + n_last > 200000) { continue; }
+        for (long long c = 0; c < n_full + n_last; ++c) {
+            const double w = (c < n_full ? gs : last) + setup;
+            const double t = pq.top() + w;
+            pq.pop();
+            pq.push(t);
+            if (t > makespan) makespan = t;
+        }
+        if (best_t < 0.0 || makespan < best_t - 1e-9) { best_t = makespan; best = gs; }
+    }
+    ctx->attn_gs[key] = best;
+    return best;
+}
+
 // one launch of the single-pass kernel on keys [key0, key0 + nkeys) of every batch item
 static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, int B, int N, int Hq, int Hkv, int key0,
                           int nkeys, const DropCfg& drop, cudaStream_t s) {
@@ -1140,19 +1179,11 @@ static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, 
     const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)(Hq + 2 * Hkv) * ATT_HD;
     CUtensorMap tq;
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
-    // query heads per CTA: the whole KV group (K / V staged once for its G heads) unless that leaves SMs without a CTA
-    // (B = 1 inference): then the group is split over several CTAs, each staging K / V itself
-    int gs = p.G;
-    {
-        const long long ctas = (long long)((N + ATT_BQ - 1) / ATT_BQ) * Hkv * B;
-        for (int d = p.G; d >= 1; --d) {
-            if (p.G % d != 0) continue;
-            gs = d;
-            if (ctas * (p.G / d) >= ctx->sm_count) break;
-        }
-    }
-    p.Gs = gs;
-    dim3 grid((N + ATT_BQ - 1) / ATT_BQ, Hkv * (p.G / gs), B);
+    const int qtiles = (N + ATT_BQ - 1) / ATT_BQ;
+    p.Gs = attention_heads_per_cta(ctx, (long long)qtiles * Hkv * B, p.G);
+    const int parts = (p.G + p.Gs - 1) / p.Gs;
+    if ((long long)B * parts > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: batch %d too large", B);
+    dim3 grid(qtiles, Hkv, B * parts);
     // key range padded to NK = 2*NKH columns (two softmax warpgroups); padded keys are masked in-kernel
     if (p.drop.thresh != 0u) {
         if (nkeys <= 64) return launch_attention<32, true>(ctx, tq, qkv, rows, cols, p, grid, s);

@@ -61,8 +61,9 @@ struct AttCfg {
 
 struct AttnParams {
     int B, N, Hq, Hkv, G;
-    int Gs;             // query heads per CTA (a divisor of G): grid.y = Hkv * G / Gs.  Gs = G stages K / V once per KV group; small
-                        // batches (B = 1 inference) use Gs < G so that the launch still fills the machine
+    int Gs;             // query heads per CTA: a KV group is cut into ceil(G / Gs) parts (the last one may be shorter), each its own
+                        // CTA staging K / V itself.  Gs = G stages K / V once per group; the host picks the Gs whose CTA list has
+                        // the shortest makespan on the SMs (attention_heads_per_cta in api.cu)
     int key0, NKeys;    // this launch attends to keys [key0, key0 + NKeys) of every batch item (NKeys <= 2 * NKH); longer
                         // sequences run one launch per key chunk and are merged by attention_combine_kernel
     __nv_bfloat16* out;
@@ -117,9 +118,12 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // (warp-uniform values go through a full-mask shuffle so that the compiler keeps the MMA issue paths on the
     //  uniform datapath -- see elect_one())
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int parts = p.G / p.Gs;
-    const int qt = blockIdx.x, g = (int)blockIdx.y / parts, b = blockIdx.z;
-    const int h0 = g * p.G + ((int)blockIdx.y % parts) * p.Gs;  // first query head of this CTA
+    // grid = (query tile, KV head, part * B + batch item): the parts of a KV group are the slowest index, so the CTAs of
+    // the full parts (Gs heads) are all handed out before those of the ragged last part (G - (parts - 1) Gs heads)
+    const int part = (int)blockIdx.z / p.B;
+    const int qt = blockIdx.x, g = blockIdx.y, b = (int)blockIdx.z % p.B;
+    const int h0 = g * p.G + part * p.Gs;             // first query head of this CTA
+    const int Gs = min(p.Gs, p.G - part * p.Gs);      // its number of heads
     const int q_row0 = b * p.N + qt * ATT_BQ;  // global token row of this tile's first query
     const int kv_row0 = b * p.N + p.key0;
     const int k_col = (p.Hq + g) * ATT_HD;
@@ -151,7 +155,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tma_load_2d(sQ, &tmap_q, &bar_q[0], h0 * ATT_HD, q_row0);
             mbar_expect_tx(bar_v, Cfg::KV_BYTES);
             for (int i = 0; i < 2; ++i) tma_load_2d(sV + i * NKH * 128, &tmap_kv, bar_v, v_col, kv_row0 + i * NKH);
-            if (p.Gs > 1) {
+            if (Gs > 1) {
                 mbar_expect_tx(&bar_q[1], ATT_Q_BYTES);
                 tma_load_2d(sQ + ATT_Q_BYTES, &tmap_q, &bar_q[1], (h0 + 1) * ATT_HD, q_row0);
             }
@@ -193,13 +197,13 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tc_fence_after();
             issue_s(0, 0);
 #pragma unroll 1
-            for (int h = 0; h < p.Gs; ++h) {
+            for (int h = 0; h < Gs; ++h) {
                 const uint32_t ph = (uint32_t)(h & 1);
                 mbar_wait_backoff(&bar_s_free[0], ph);  // S_A(h) is in registers -> the S region is free
                 tc_fence_after();
                 issue_s(h, 1);
                 if (lane == 0) ATT_TRACE(4 * h + 0);
-                if (h + 1 < p.Gs) {
+                if (h + 1 < Gs) {
                     mbar_wait_backoff(&bar_q[(h + 1) & 1], (uint32_t)(((h + 1) >> 1) & 1));
                     mbar_wait_backoff(&bar_s_free[1], ph);  // S_B(h) is in registers
                     tc_fence_after();
@@ -229,7 +233,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             };
             mbar_wait_backoff(bar_v, 0);
 #pragma unroll 1
-            for (int h = 0; h < p.Gs; ++h) {
+            for (int h = 0; h < Gs; ++h) {
                 const uint32_t ph = (uint32_t)(h & 1);
                 if (h > 0) mbar_wait_backoff(bar_o_free, (uint32_t)((h - 1) & 1));  // O(h-1) has left TMEM
                 mbar_wait_backoff(&bar_p_full[0], ph);
@@ -244,7 +248,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         } else if (warp == 14 && lane == 0) {
             // Q(h+2) into stage (h & 1) once S_B(h), the last reader of that stage, has retired
 #pragma unroll 1
-            for (int h = 0; h + 2 < p.Gs; ++h) {
+            for (int h = 0; h + 2 < Gs; ++h) {
                 mbar_wait_backoff(&bar_s_full[1], (uint32_t)(h & 1));
                 mbar_expect_tx(&bar_q[h & 1], ATT_Q_BYTES);
                 tma_load_2d(sQ + (h & 1) * ATT_Q_BYTES, &tmap_q, &bar_q[h & 1], (h0 + h + 2) * ATT_HD, q_row0);
@@ -259,7 +263,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const bool row_ok = qt * ATT_BQ + r < p.N;
         __nv_bfloat16* out_row = p.out + (long long)(q_row0 + r) * (p.Hq * ATT_HD) + (long long)h0 * ATT_HD;
 #pragma unroll 1
-        for (int h = 0; h < p.Gs; ++h) {
+        for (int h = 0; h < Gs; ++h) {
             mbar_wait_backoff(bar_o_full, (uint32_t)(h & 1));
             tc_fence_after();
             const float2 sa = stats[(h & 1) * 2 * ATT_BQ + r];
@@ -305,7 +309,7 @@ gqa_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         // dropout mask row of (b, first head of the group, this query); + h * N per head
         const uint32_t drop_row = (uint32_t)(((long long)b * p.Hq + h0) * p.N + qt * ATT_BQ + r);
 #pragma unroll 1
-        for (int h = 0; h < p.Gs; ++h) {
+        for (int h = 0; h < Gs; ++h) {
             mbar_wait(&bar_s_full[half], (uint32_t)(h & 1));
             if (trace_thr) ATT_TRACE(32 + 32 * half + 4 * h + 0);
             tc_fence_after();

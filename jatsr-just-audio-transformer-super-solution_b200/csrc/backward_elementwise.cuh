@@ -374,6 +374,7 @@ adaln_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int AGS_ROWS = 2;
 constexpr int AGS_STAGES = 3;
+constexpr int AGS_PAD = 512;  // bytes behind the last stage
 
 template <int NORM_KIND, int HAS_GATE, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 320 ? 2 : 1)
@@ -383,11 +384,12 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
                              float* __restrict__ dweight, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
                              __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, float* __restrict__ dbias, DropCfg drop,
                              const float* __restrict__ rowscale, int D, int tokens_per_batch, int rows_per_cta) {
-    constexpr int R = AGS_ROWS, S = AGS_STAGES;
-    extern __shared__ __align__(128) uint8_t ags_smem[];
+    constexpr int R = AGS_ROWS, S = AGS_STAGES, NW = MAXT / 32;
+    static_assert(R == 2, "the partial sums of a group travel as one float4");
+    extern __shared__ __align__(128) uint8_t ags_smem[];  // S stages + AGS_PAD bytes (threads past D / 4 read, and discard, a few bytes past the last row)
     __shared__ uint64_t full[S];
-    __shared__ float4 red[2][16];  // [buffer][warp] = (sum g, sum g xhat) of the R = 2 rows of a group
-    const int c4 = threadIdx.x, lane = c4 & 31, warp = c4 >> 5, nw = (int)(blockDim.x >> 5);
+    __shared__ float4 red[2][NW];  // [buffer][warp] = (sum g, sum g xhat) of the two rows of a group
+    const int c4 = threadIdx.x, lane = c4 & 31, warp = c4 >> 5;
     const bool act = c4 < (D >> 2);
     const int b = (int)(gridDim.y - 1 - blockIdx.y);  // last rows first, as above
     const float inv_d = 1.0f / (float)D;
@@ -415,6 +417,7 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
         fence_barrier_init();
         for (int g = 0; g < S && g < groups; ++g) issue(g);
     }
+    if (c4 < 2 * NW) red[c4 / NW][c4 % NW] = make_float4(0.f, 0.f, 0.f, 0.f);  // entries of warps this launch does not have
     float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), w4 = sc4, g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float rs = 1.0f;
     if (act) {
@@ -433,6 +436,8 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
 #pragma unroll
     for (int r = 0; r < R; ++r) st_next[r] = n0 + r < n1 ? __ldg(rowstats + row0 + n0 + r) : make_float2(0.f, 0.f);
     __syncthreads();  // barrier initialisation visible before anybody waits
+    // smem offsets of this thread's 4 columns inside a stage (f32 rows: 16 bytes per thread, bf16 rows: 8)
+    const uint32_t cx = (uint32_t)c4 * 16u, ch = (uint32_t)c4 * 8u;
     int buf = 0;
     for (int g = 0; g < groups; ++g) {
         const int n = n0 + g * R;
@@ -444,21 +449,35 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
         }
         mbar_wait(&full[g % S], (uint32_t)((g / S) & 1));
         const uint8_t* st = ags_smem + (size_t)(g % S) * stage_bytes;
+        // loads are unconditional (a row past the CTA's range holds stale or uninitialised bytes, a thread past D / 4 reads its
+        // neighbours' columns); what is invalid is replaced by zeros with selects, so the loop body has no branches
         float4 xv[R], gv[R], ov[R];
         uint2 yv[R];
+        bool ok[R];
         float sg[R], sgx[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const bool ok = act && n + r < n1;
-            const float4 xr = ok ? reinterpret_cast<const float4*>(st + (size_t)r * D * 4)[c4] : zero4;
-            ov[r] = ok ? reinterpret_cast<const float4*>(st + off_dx + (size_t)r * D * 4)[c4] : zero4;
-            const float4 d = ok ? bf16x4_to_f32(reinterpret_cast<const uint2*>(st + off_dh + (size_t)r * D * 2)[c4]) : zero4;
-            if (HAS_GATE) yv[r] = ok ? reinterpret_cast<const uint2*>(st + off_y + (size_t)r * D * 2)[c4] : make_uint2(0u, 0u);
+            ok[r] = act && n + r < n1;
+            float4 xr = *reinterpret_cast<const float4*>(st + (uint32_t)(r * D) * 4u + cx);
+            float4 o4 = *reinterpret_cast<const float4*>(st + off_dx + (uint32_t)(r * D) * 4u + cx);
+            uint2 dr = *reinterpret_cast<const uint2*>(st + off_dh + (uint32_t)(r * D) * 2u + ch);
+            if (HAS_GATE) {
+                const uint2 yr = *reinterpret_cast<const uint2*>(st + off_y + (uint32_t)(r * D) * 2u + ch);
+                yv[r] = ok[r] ? yr : make_uint2(0u, 0u);
+            }
+            dr = ok[r] ? dr : make_uint2(0u, 0u);
+            ov[r] = ok[r] ? o4 : zero4;
+            const float4 d = bf16x4_to_f32(dr);
             const float mean = stt[r].x, rstd = stt[r].y;
-            const float4 xh = ok ? make_float4((xr.x - mean) * rstd, (xr.y - mean) * rstd, (xr.z - mean) * rstd, (xr.w - mean) * rstd) : zero4;
+            float4 xh = make_float4((xr.x - mean) * rstd, (xr.y - mean) * rstd, (xr.z - mean) * rstd, (xr.w - mean) * rstd);
+            xh = ok[r] ? xh : zero4;
             xv[r] = xh;
             a_shift.x += d.x; a_shift.y += d.y; a_shift.z += d.z; a_shift.w += d.w;
-            a_scale.x += d.x * xh.x * w4.x; a_scale.y += d.y * xh.y * w4.y; a_scale.z += d.z * xh.z * w4.z; a_scale.w += d.w * xh.w * w4.w;
+            if (NORM_KIND == 1) {
+                a_scale.x += d.x * xh.x * w4.x; a_scale.y += d.y * xh.y * w4.y; a_scale.z += d.z * xh.z * w4.z; a_scale.w += d.w * xh.w * w4.w;
+            } else {
+                a_scale.x += d.x * xh.x; a_scale.y += d.y * xh.y; a_scale.z += d.z * xh.z; a_scale.w += d.w * xh.w;
+            }
             float4 gg = make_float4(d.x * sc4.x, d.y * sc4.y, d.z * sc4.z, d.w * sc4.w);
             if (NORM_KIND == 1) {
                 a_w.x += gg.x * xh.x; a_w.y += gg.y * xh.y; a_w.z += gg.z * xh.z; a_w.w += gg.w * xh.w;
@@ -480,7 +499,8 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
         __syncthreads();  // every thread holds its part of the stage in registers: the stage can be refilled
         if (threadIdx.x == 0 && g + S < groups) issue(g + S);
         float4 tot = zero4;
-        for (int w = 0; w < nw; ++w) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
             const float4 p0 = red[buf][w];
             tot.x += p0.x; tot.y += p0.y; tot.z += p0.z; tot.w += p0.w;
         }
@@ -489,19 +509,18 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
         const float mgxs[R] = {tot.y * inv_d, tot.w * inv_d};
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (!(act && n + r < n1)) continue;
             const long long row = row0 + n + r;
-            const float mg = NORM_KIND == 0 ? mgs[r] : 0.0f, mgx = mgxs[r], rd = stt[r].y;
+            const float mg = NORM_KIND == 0 ? mgs[r] : 0.0f, mgx = mgxs[r], rd = stt[r].y;  // rd = 0 for a row past the range
             float4 o;
             o.x = rd * (gv[r].x - mg - xv[r].x * mgx) + ov[r].x;
             o.y = rd * (gv[r].y - mg - xv[r].y * mgx) + ov[r].y;
             o.z = rd * (gv[r].z - mg - xv[r].z * mgx) + ov[r].z;
             o.w = rd * (gv[r].w - mg - xv[r].w * mgx) + ov[r].w;
-            reinterpret_cast<float4*>(dx + row * D)[c4] = o;
+            if (ok[r]) reinterpret_cast<float4*>(dx + row * D)[c4] = o;
             if (HAS_GATE) {
                 const float4 yf = bf16x4_to_f32(yv[r]);
                 a_gate.x += o.x * yf.x; a_gate.y += o.y * yf.y; a_gate.z += o.z * yf.z; a_gate.w += o.w * yf.w;
-                float4 dm = o;
+                float4 dm = ok[r] ? o : zero4;
                 if (drop.thresh != 0u) {
                     const uint32_t rr = (uint32_t)row, cc = (uint32_t)(c4 * 4);
                     float m0, m1, m2, m3;
@@ -510,8 +529,9 @@ adaln_gate_bwd_staged_kernel(const __nv_bfloat16* __restrict__ dh, const float* 
                     dm.x *= m0; dm.y *= m1; dm.z *= m2; dm.w *= m3;
                 }
                 a_sum.x += dm.x; a_sum.y += dm.y; a_sum.z += dm.z; a_sum.w += dm.w;
-                reinterpret_cast<uint2*>(dy + row * D)[c4] =
-                    make_uint2(pack_bf16(dm.x * g4.x, dm.y * g4.y), pack_bf16(dm.z * g4.z, dm.w * g4.w));
+                if (ok[r])
+                    reinterpret_cast<uint2*>(dy + row * D)[c4] =
+                        make_uint2(pack_bf16(dm.x * g4.x, dm.y * g4.y), pack_bf16(dm.z * g4.z, dm.w * g4.w));
             }
         }
     }

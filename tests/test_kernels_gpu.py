@@ -375,7 +375,11 @@ def test_gemm_multicast_cluster_is_bit_identical(ops, L, kind, M):
 
 
 # ------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 16, 4), (2, 256, 4, 4), (1, 352, 5, 1)])
+# heads per CTA picked by the launch's makespan model: B = 28 -> parts of 3 + 2 heads, B = 8 -> 4 + 1, B = 4 -> 2 + 2 + 1,
+# B = 56 -> whole groups (5), B <= 2 -> single heads; (6, 100, 7, 1): 7 heads in ragged parts
+@pytest.mark.parametrize("B,N,Hq,Hkv", [(2, 345, 20, 4), (1, 22, 8, 4), (3, 129, 16, 4), (2, 256, 4, 4), (1, 352, 5, 1),
+                                        (28, 345, 20, 4), (8, 345, 20, 4), (4, 345, 20, 4), (56, 345, 20, 4), (6, 100, 7, 1),
+                                        (40, 130, 7, 1)])
 def test_gqa_attention(ops, B, N, Hq, Hkv):
     torch.manual_seed(8)
     hd = 64
