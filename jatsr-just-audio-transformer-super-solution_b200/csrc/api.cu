@@ -1134,14 +1134,17 @@ extern "C" int jat_gqa_attention_fwd(jat_ctx* ctx, const void* qkv, void* out, f
 // Query heads per CTA.  A CTA serves Gs heads of one (query tile, KV group) after staging the group's K / V once; the
 // launch is `groups` x ceil(G / Gs) CTAs, one per SM at a time (512 TMEM columns), handed out full parts first.  Whole
 // groups (Gs = G) stage K / V least often, but 336 CTAs of 5 heads on 148 SMs (training, B = 28) take 3 rounds for 2.27
-// rounds of work; parts of 3 + 2 heads finish in 12.9 head-times instead of 15.  Pick the Gs with the shortest list-schedule
-// makespan, a CTA costing (heads + 0.4) head-times (0.4: barrier / TMEM set-up and the K / V + first Q load before the first MMA).
+// rounds of work.  Pick the Gs with the shortest list-schedule makespan, a CTA costing (heads + 0.6) head-times -- 0.6 for
+// barrier / TMEM set-up and the K / V + first Q load before the first MMA, fitted to the training step's measured class
+// times (Gs = 5: 3.19 ms, 4: 2.87, 3: 2.92, 2: 3.05; JAT_ATTN_GS forces a value for such sweeps).
 static int attention_heads_per_cta(jat_ctx* ctx, long long groups, int G) {
+    static const int forced = [] { const char* v = getenv("JAT_ATTN_GS"); return v ? atoi(v) : 0; }();   // experiments
+    if (forced > 0) return forced < G ? forced : G;
     const long long key = groups * 64 + G;
     auto it = ctx->attn_gs.find(key);
     if (it != ctx->attn_gs.end()) return it->second;
     const int sms = ctx->sm_count;
-    const double setup = 0.4;
+    const double setup = 0.6;
     int best = G;
     double best_t = -1.0;
     for (int gs = G; gs >= 1; --gs) {

@@ -648,6 +648,30 @@ def test_adaln_gate_bwd_fused_matches_autograd(ops, L, norm_kind, D, B, Ntok, ga
         assert rel_l2(dw, w.grad) < 1e-5
 
 
+@pytest.mark.parametrize("D,B,Ntok", [(1280, 28, 345), (128, 3, 22), (2048, 2, 40)])
+def test_adaln_gate_bwd_rows_are_bitwise_reproducible(ops, D, B, Ntok):
+    """dx and dy are written once per element (no atomics): two launches on the same inputs must agree bit for bit.  A race
+    in the shared-memory staging (a stage refilled while still being read, a barrier phase off by one) would show up here."""
+    torch.manual_seed(3)
+    M = B * Ntok
+    x = torch.randn(M, D, device=dev()) * 1.3 + 0.2
+    rowstats = torch.stack([x.mean(-1), torch.rsqrt(x.var(-1, unbiased=False) + 1e-6)], -1).contiguous()
+    mod = 0.3 * torch.randn(B, 3 * D, device=dev())
+    dh = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+    yb = torch.randn(M, D, device=dev()).to(torch.bfloat16)
+    base = torch.randn(M, D, device=dev())
+    outs = []
+    for _ in range(3):
+        dmod = torch.zeros(B, 3 * D, device=dev())
+        dx = base.clone()
+        dy = ops.adaln_gate_bwd(dh, x, rowstats, B, Ntok, dx, scale=mod[:, D:2 * D], mod_batch_stride=3 * D, dshift=dmod[:, :D],
+                                dscale=dmod[:, D:2 * D], dmod_batch_stride=3 * D, y=yb, gate=mod[:, 2 * D:], dgate=dmod[:, 2 * D:],
+                                drop_p=0.1, drop_seed=11)
+        outs.append((dx, dy))
+    for dx, dy in outs[1:]:
+        assert torch.equal(dx, outs[0][0]) and torch.equal(dy, outs[0][1])
+
+
 def test_colsum_and_cast(ops):
     torch.manual_seed(23)
     a = torch.randn(9660, 512, device=dev()).to(torch.bfloat16)

@@ -171,8 +171,12 @@ def test_zero_copy_gradient_handoff_matches_copy_and_guards_against_aliasing():
             loss = torch.nn.functional.mse_loss(m(z_t, t, lr), hr)
             loss.backward()
             losses.append(loss.item())
-        for p, q in zip(models[0].parameters(), models[1].parameters()):
-            assert rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-5   # f32 atomics in the column sums only
+        for (name, p), q in zip(models[0].named_parameters(), models[1].parameters()):
+            err = rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy())
+            # step 0: same parameters, the only difference is the order of the f32 atomics in the column sums.  Later steps:
+            # Adam's g / sqrt(v) turns a last-bit difference of a near-zero gradient into a finite parameter difference, so the
+            # two trajectories drift apart at the rate any two runs of ONE model do (seen: 2e-4 at step 2)
+            assert err < (1e-5 if step == 0 else 2e-3), (step, name, err)
         packed = models[1]._engine.grads(dev()).by_param
         assert all(q.grad.data_ptr() == packed[q].data_ptr() for q in models[1].parameters())   # really zero-copy
         assert abs(losses[0] - losses[1]) <= 1e-4 * max(1.0, losses[0])
