@@ -1415,7 +1415,6 @@ extern "C" int jat_dit_forward_train(jat_ctx* ctx, const jat_dit_weights* w, con
     const int M = B * N, Hq = w->n_q_heads, Hkv = w->n_kv_heads;
     const int Cc = w->cond_channels > 0 ? w->cond_channels : C;
     const int QKV = (Hq + 2 * Hkv) * 64, KIN = (C + Cc) * P, NM = w->depth * 6 * D;
-    cudaStream_t s = (cudaStream_t)stream;
     jat_gemm_epilogue e;
     // ---- train-mode regularisers: Dropout(p) on attention probabilities / GELU output / mlp.3 output, DropPath per block
     const float pd = sv->dropout_p;
