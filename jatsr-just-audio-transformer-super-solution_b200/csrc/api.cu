@@ -1184,6 +1184,7 @@ static int attention_pass(jat_ctx* ctx, const void* qkv, void* out, float* lse, 
     JAT_TRY(make_tmap(ctx, &tq, qkv, rows, cols, cols, ATT_BQ));
     const int qtiles = (N + ATT_BQ - 1) / ATT_BQ;
     p.Gs = attention_heads_per_cta(ctx, (long long)qtiles * Hkv * B, p.G);
+    if ((long long)B * ((p.G + p.Gs - 1) / p.Gs) > 65535) p.Gs = p.G;   // grid.z limit: whole groups
     const int parts = (p.G + p.Gs - 1) / p.Gs;
     if ((long long)B * parts > 65535) return fail(JAT_ERR_BAD_SHAPE, "jat_gqa_attention_fwd: batch %d too large", B);
     dim3 grid(qtiles, Hkv, B * parts);
